@@ -1,0 +1,161 @@
+// CUDA-core convolution kernels.
+//  * k_conv_simt<T>: the same tap-GEMM the tcgen05 kernel computes, on FP32 FMA units.  T = float is the
+//    PREC_FP32_SIMT precision mode (bit-for-bit independent check of the layer graph against the oracle);
+//    T = __half reads the very same fp16 buffers/rounding points as the tcgen05 path (PREC_FP16_SIMT), which
+//    isolates tensor-core descriptor bugs from precision effects.
+//  * k_head / k_tail: the 1->C and C->1 3x3 convs of models/ResUNet.py:11,24 in fp32 (SURVEY.md section 0.8:
+//    these two layers dominate the rounding error, and are 0.2 % of the FLOPs).
+#include "conv_epilogue.cuh"
+#include "kernels.cuh"
+#include "launch.cuh"
+
+namespace gd {
+
+constexpr int SIMT_KSLAB = 256;
+
+template <typename T> __device__ __forceinline__ void load_vec(const T* p, float* a);
+template <> __device__ __forceinline__ void load_vec<float>(const float* p, float* a) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+}
+template <> __device__ __forceinline__ void load_vec<__half>(const __half* p, float* a) {
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); a[2 * i] = f.x; a[2 * i + 1] = f.y; }
+}
+
+// weights: [tap][Kt][N] of T
+template <typename T>
+__global__ void __launch_bounds__(128) k_conv_simt(const ConvParams p) {
+    constexpr int CH = ActT<T>::CH;
+    __shared__ __align__(16) float wsm[SIMT_KSLAB * 16];
+    const int m = blockIdx.x * MTILE + threadIdx.x;
+    const int n0 = blockIdx.y * 16;
+    const T* A = reinterpret_cast<const T*>(p.a);
+    const T* Wt = reinterpret_cast<const T*>(p.w);
+    const int row = p.g.base0 + m;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int tap = 0; tap < p.ntaps; ++tap) {
+        for (int k0 = 0; k0 < p.Kt; k0 += SIMT_KSLAB) {
+            const int kn = min(SIMT_KSLAB, p.Kt - k0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < kn * 16; i += blockDim.x)
+                wsm[i] = (float)Wt[((size_t)tap * p.Kt + k0 + (i >> 4)) * p.N + n0 + (i & 15)];
+            __syncthreads();
+            const T* ap = A + ((size_t)(k0 / CH) * p.g.Ptot + row + p.off[tap]) * CH;
+            for (int kc = 0; kc < kn / CH; ++kc) {
+                float a[CH];
+                load_vec<T>(ap + (size_t)kc * p.g.Ptot * CH, a);
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const float4* wr = reinterpret_cast<const float4*>(wsm + (kc * CH + j) * 16);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 w4 = wr[q];
+                        acc[4 * q] = fmaf(a[j], w4.x, acc[4 * q]);
+                        acc[4 * q + 1] = fmaf(a[j], w4.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(a[j], w4.z, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(a[j], w4.w, acc[4 * q + 3]);
+                    }
+                }
+            }
+        }
+    }
+    RowCtx rc = make_row_ctx(p, m);
+    if (rc.valid) epilogue_store16<T>(p, rc, n0, acc);
+}
+
+// head: t [B][48*48] fp32 (already scaled per stamp) -> skip32 (fp32) + x16 (operand precision), C0 channels.
+// weights w[tap][C0] fp32.
+template <typename T>
+__global__ void __launch_bounds__(128) k_head(const float* __restrict__ t, const float* __restrict__ w, int C0,
+                                              ConvParams p, int batch) {
+    extern __shared__ float wsm[];           // 9*C0
+    for (int i = threadIdx.x; i < 9 * C0; i += blockDim.x) wsm[i] = w[i];
+    __syncthreads();
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * NPIX) return;
+    int b = idx / NPIX, r = idx - b * NPIX, y = r / STAMP, x = r - y * STAMP;
+    float in[9];
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            int yy = y + dy, xx = x + dx;
+            in[(dy + 1) * 3 + dx + 1] = (yy >= 0 && yy < STAMP && xx >= 0 && xx < STAMP) ? t[(size_t)b * NPIX + yy * STAMP + xx] : 0.f;
+        }
+    RowCtx rc;
+    rc.valid = true; rc.row = p.g.base0 + b * p.g.S + y * p.g.Wp + x; rc.crow = 0; rc.ctap = 0; rc.frow0 = 0;
+    for (int n0 = 0; n0 < C0; n0 += 16) {
+        float acc[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp) s = fmaf(in[tp], wsm[tp * C0 + n0 + c], s);
+            acc[c] = s;
+        }
+        epilogue_store16<T>(p, rc, n0, acc);
+    }
+}
+
+// tail: x32 [C0/4][Ptot][4] fp32 -> z [B][48*48] fp32, times the per-stamp power-of-two scale.
+__global__ void __launch_bounds__(128) k_tail(const float* __restrict__ x32, const float* __restrict__ w, int C0, Geom g,
+                                              const float* __restrict__ tscale, float* __restrict__ z, int batch) {
+    extern __shared__ float wsm[];           // 9*C0
+    for (int i = threadIdx.x; i < 9 * C0; i += blockDim.x) wsm[i] = w[i];
+    __syncthreads();
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * NPIX) return;
+    int b = idx / NPIX, r = idx - b * NPIX, y = r / STAMP, x = r - y * STAMP;
+    int row = g.base0 + b * g.S + y * g.Wp + x;
+    float s = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            int yy = y + dy, xx = x + dx;
+            if (yy < 0 || yy >= STAMP || xx < 0 || xx >= STAMP) continue;
+            const float* wp = wsm + ((dy + 1) * 3 + dx + 1) * C0;
+            const float* xp = x32 + (size_t)(row + dy * g.Wp + dx) * 4;
+            for (int c4 = 0; c4 < C0 / 4; ++c4) {
+                float4 v = *reinterpret_cast<const float4*>(xp + (size_t)c4 * g.Ptot * 4);
+                s = fmaf(v.x, wp[4 * c4], s); s = fmaf(v.y, wp[4 * c4 + 1], s);
+                s = fmaf(v.z, wp[4 * c4 + 2], s); s = fmaf(v.w, wp[4 * c4 + 3], s);
+            }
+        }
+    z[idx] = s * tscale[b];
+}
+
+// ---- host launchers ----
+int launch_conv_simt(const ConvParams& p, int prec, cudaStream_t st) {
+    if (p.g.M <= 0) return GD_OK;
+    dim3 grid((p.g.M + MTILE - 1) / MTILE, p.N / 16);
+    if (prec == PREC_FP32_SIMT) k_conv_simt<float><<<grid, 128, 0, st>>>(p);
+    else k_conv_simt<__half><<<grid, 128, 0, st>>>(p);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+
+int launch_head(const float* t, const float* w, int C0, const ConvParams& p, int batch, int prec, cudaStream_t st) {
+    int n = batch * NPIX, blocks = (n + 127) / 128;
+    if (n <= 0) return GD_OK;
+    if (prec == PREC_FP32_SIMT) k_head<float><<<blocks, 128, 9 * C0 * sizeof(float), st>>>(t, w, C0, p, batch);
+    else k_head<__half><<<blocks, 128, 9 * C0 * sizeof(float), st>>>(t, w, C0, p, batch);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+
+int launch_tail(const float* x32, const float* w, int C0, const Geom& g, const float* tscale, float* z, int batch,
+                cudaStream_t st) {
+    int n = batch * NPIX, blocks = (n + 127) / 128;
+    if (n <= 0) return GD_OK;
+    k_tail<<<blocks, 128, 9 * C0 * sizeof(float), st>>>(x32, w, C0, g, tscale, z, batch);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+
+}  // namespace gd

@@ -1,0 +1,623 @@
+// Per-stamp shared-memory FFT kernels: everything in the hot path that the reference does with torch.fft.
+//   path G  (models/unrolled_admm_gaussian.py): k_g_prologue (:118-123 + init_l2 :111-115), k_g_xupdate
+//           (XUpdateGaussian :89-93 fused with the dual update :145 and the denoiser-input scaling of :142)
+//   path U  (models/Unrolled_ADMM.py): k_u_prologue (:181-196 + init_l2 :170-175), k_u_pre (V-update :207,
+//           denoiser input :208), k_u_post (X-update :209 -> effective :315-319, duals :212-213)
+//   solvers (models/Richard_Lucy.py:10-24, models/Wiener.py:10-20, models/Tikhonet.py:15-31)
+// One CTA owns one stamp; the stamp, its spectrum and the PSF spectrum never leave shared memory inside a kernel.
+//
+// Index conventions (see fft_core.cuh): spectra are half spectra S[s1][k2], k2 natural in [0, N/2], s1 the
+// digit-swapped slot of frequency k1 = freq(s1).  The reference's pad_double + ifftshift (path G) and
+// psf_to_otf == roll(N/2) (path U / solvers) are pure phase factors on the spectrum of the image placed at the
+// corner of the grid:  shift by 72 on a 96 grid -> (+i)^(k1+k2), shift by 24 on a 48 grid -> (-1)^(k1+k2).
+#include <math.h>
+#include "fft_block.cuh"
+#include "launch.cuh"
+
+namespace gd {
+
+// =====================================================================================================
+// Path G
+// =====================================================================================================
+using FG96 = Real2D<96, 8, 12, 48>;
+constexpr int SPG = 50;
+constexpr int G_THREADS = 256;
+constexpr size_t G_SMEM_PRO = (size_t)(24 * 96 + 2 * 96 * SPG + 96) * sizeof(float2) + 64;
+constexpr size_t G_SMEM_XUP = (size_t)(24 * 96 + 96 * SPG + 96) * sizeof(float2) + 64;
+
+// y, psf -> Pc = (-i)^(k1+k2) conj(Hc) Yc, HtH = |Hc|^2 (workspace), z0 = init_l2, u = 0
+__global__ void __launch_bounds__(G_THREADS) k_g_prologue(const float* __restrict__ y, const float* __restrict__ psf,
+                                                          const float* __restrict__ alpha, float2* __restrict__ Pc,
+                                                          float* __restrict__ HtH, float* __restrict__ z,
+                                                          float* __restrict__ u, float* __restrict__ x) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Z = reinterpret_cast<float2*>(smem_raw);
+    float2* SY = Z + 24 * 96;
+    float2* SH = SY + 96 * SPG;
+    float2* tw = SH + 96 * SPG;
+    const int b = blockIdx.x;
+    const float* yb = y + (size_t)b * NPIX;
+    const float* kb = psf + (size_t)b * NPIX;
+    fill_twiddles<96>(tw);
+    for (int i = threadIdx.x; i < 24 * 48; i += blockDim.x) {
+        int j = i / 48, c = i - j * 48;
+        Z[j * 96 + c] = make_float2(fmaxf(yb[(2 * j) * 48 + c], 0.f), fmaxf(yb[(2 * j + 1) * 48 + c], 0.f));   // :118
+    }
+    fwd2d<FG96, SPG>(Z, SY, tw);
+    for (int i = threadIdx.x; i < 24 * 48; i += blockDim.x) {
+        int j = i / 48, c = i - j * 48;
+        Z[j * 96 + c] = make_float2(kb[(2 * j) * 48 + c], kb[(2 * j + 1) * 48 + c]);
+    }
+    fwd2d<FG96, SPG>(Z, SH, tw);
+    const float ia = 1.0f / alpha[b];
+    float2* Pb = Pc + (size_t)b * FG_SPEC;
+    float* Hb = HtH + (size_t)b * FG_SPEC;
+    for (int q = threadIdx.x; q < FG_SPEC; q += blockDim.x) {
+        int s1 = q / FG_NH, k2 = q - s1 * FG_NH;
+        float2 h = SH[s1 * SPG + k2], yy = SY[s1 * SPG + k2];
+        float2 p = mul_negi_pow(cmul(cconj(h), yy), FG96::L::freq(s1) + k2);
+        float hh = h.x * h.x + h.y * h.y;
+        Pb[q] = p;
+        Hb[q] = hh;
+        float d = 1.0f / (hh + ia);                                                                           // :112-113
+        SY[s1 * SPG + k2] = make_float2(p.x * d, p.y * d);
+    }
+    inv2d<FG96, SPG>(SY, Z, tw);
+    const float sc = 1.0f / (96.f * 96.f);
+    for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+        int r = i / 48, c = i - r * 48;
+        z[(size_t)b * NPIX + i] = zpix<96>(Z, r, c) * sc;
+        u[(size_t)b * NPIX + i] = 0.f;                                                                        // :130
+        x[(size_t)b * NPIX + i] = 0.f;
+    }
+}
+
+// iteration `it`:  u <- u + rho_{it-1} (x_prev - z)   (it > 0; the dual update of the previous iteration, :145)
+//                  x <- crop(ifft((Pc + F(rho z - u)) / (rho + HtH)))                                    (:89-93)
+//                  t <- (rho x + u) * 2^-e, tscale = 2^e                                   (denoiser input, :142)
+__global__ void __launch_bounds__(G_THREADS) k_g_xupdate(const float2* __restrict__ Pc, const float* __restrict__ HtH,
+                                                         const float* __restrict__ rho, int n_rho, int it,
+                                                         const float* __restrict__ z, float* __restrict__ x,
+                                                         float* __restrict__ u, float* __restrict__ t,
+                                                         float* __restrict__ tscale) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Z = reinterpret_cast<float2*>(smem_raw);
+    float2* S = Z + 24 * 96;
+    float2* tw = S + 96 * SPG;
+    float* red = reinterpret_cast<float*>(tw + 96);
+    const int b = blockIdx.x;
+    const size_t o = (size_t)b * NPIX;
+    const float r_now = rho[(size_t)b * n_rho + it];
+    const float r_prev = it > 0 ? rho[(size_t)b * n_rho + it - 1] : 0.f;
+    fill_twiddles<96>(tw);
+    constexpr int PER = NPIX / G_THREADS;      // 9
+    float ureg[PER];
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        int i = threadIdx.x + e * G_THREADS;
+        int r = i / 48, c = i - r * 48;
+        float zz = z[o + i], uu = u[o + i];
+        if (it > 0) uu = uu + r_prev * (x[o + i] - zz);
+        ureg[e] = uu;
+        zpix<96>(Z, r, c) = r_now * zz - uu;
+    }
+    fwd2d<FG96, SPG>(Z, S, tw);
+    const float2* Pb = Pc + (size_t)b * FG_SPEC;
+    const float* Hb = HtH + (size_t)b * FG_SPEC;
+    for (int q = threadIdx.x; q < FG_SPEC; q += blockDim.x) {
+        int s1 = q / FG_NH, k2 = q - s1 * FG_NH;
+        float2 v = S[s1 * SPG + k2], p = Pb[q];
+        float d = 1.0f / (r_now + Hb[q]);
+        S[s1 * SPG + k2] = make_float2((p.x + v.x) * d, (p.y + v.y) * d);
+    }
+    inv2d<FG96, SPG>(S, Z, tw);
+    const float sc = 1.0f / (96.f * 96.f);
+    float tv[PER], amax = 0.f;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        int i = threadIdx.x + e * G_THREADS;
+        int r = i / 48, c = i - r * 48;
+        float xx = zpix<96>(Z, r, c) * sc;
+        x[o + i] = xx;
+        u[o + i] = ureg[e];
+        tv[e] = r_now * xx + ureg[e];
+        amax = fmaxf(amax, fabsf(tv[e]));
+    }
+    amax = block_max(amax, red);
+    float inv;
+    float s = pow2_scale(amax, &inv);
+    if (threadIdx.x == 0) tscale[b] = s;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) t[o + threadIdx.x + e * G_THREADS] = tv[e] * inv;
+}
+
+// analysis=True bookkeeping (:147-152): u_i = u + rho_i (x_i - z_i) written to the analysis buffer
+__global__ void k_g_dual_out(const float* __restrict__ rho, int n_rho, int it, const float* __restrict__ x,
+                             const float* __restrict__ z, const float* __restrict__ u, float* __restrict__ uo, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int b = i / NPIX;
+    uo[i] = u[i] + rho[(size_t)b * n_rho + it] * (x[i] - z[i]);
+}
+
+// plain scaling of an arbitrary single-channel stamp batch for gd_resunet_forward
+__global__ void __launch_bounds__(G_THREADS) k_scale_in(const float* __restrict__ in, float* __restrict__ t,
+                                                        float* __restrict__ tscale) {
+    __shared__ float red[G_THREADS / 32];
+    const size_t o = (size_t)blockIdx.x * NPIX;
+    float v[NPIX / G_THREADS], amax = 0.f;
+#pragma unroll
+    for (int e = 0; e < NPIX / G_THREADS; ++e) { v[e] = in[o + threadIdx.x + e * G_THREADS]; amax = fmaxf(amax, fabsf(v[e])); }
+    amax = block_max(amax, red);
+    float inv;
+    float s = pow2_scale(amax, &inv);
+    if (threadIdx.x == 0) tscale[blockIdx.x] = s;
+#pragma unroll
+    for (int e = 0; e < NPIX / G_THREADS; ++e) t[o + threadIdx.x + e * G_THREADS] = v[e] * inv;
+}
+
+__global__ void k_fill_rho(const float* __restrict__ src, int n_rho, float* __restrict__ rho, int batch) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < batch * n_rho) rho[i] = src[i % n_rho];
+}
+
+// =====================================================================================================
+// 48x48 circular transforms: path U and the classical solvers
+// =====================================================================================================
+using FU48 = Real2D<48, 4, 12, 48>;
+constexpr int SPU = 26;
+constexpr int U_THREADS = 128;
+constexpr int U_PER = NPIX / U_THREADS;        // 18
+constexpr int ZU = 24 * 48;                    // float2 per packed stamp
+constexpr int SU = 48 * SPU;                   // float2 per spectrum buffer
+
+__device__ __forceinline__ void load_packed48(float2* Z, const float* __restrict__ src, float mul, bool clamp) {
+    for (int i = threadIdx.x; i < ZU; i += blockDim.x) {
+        int j = i / 48, c = i - j * 48;
+        float a = src[(2 * j) * 48 + c], bb = src[(2 * j + 1) * 48 + c];
+        if (clamp) { a = fmaxf(a, 0.f); bb = fmaxf(bb, 0.f); }
+        Z[i] = make_float2(a * mul, bb * mul);
+    }
+}
+__device__ __forceinline__ float sgn48(int s1, int k2) { return ((FU48::L::freq(s1) + k2) & 1) ? -1.f : 1.f; }
+
+// H = fft2(roll(psf, 24, 24)) = (-1)^(k1+k2) Hc   (psf_to_otf, utils/utils_torch.py:79-92, same-size kernel)
+__device__ __forceinline__ void otf48(const float* __restrict__ psf, float2* Z, float2* SH, const float2* tw) {
+    load_packed48(Z, psf, 1.f, false);
+    fwd2d<FU48, SPU>(Z, SH, tw);
+    for (int q = threadIdx.x; q < FU_SPEC; q += blockDim.x) {
+        int s1 = q / FU_NH, k2 = q - s1 * FU_NH;
+        float sg = sgn48(s1, k2);
+        float2 h = SH[s1 * SPU + k2];
+        SH[s1 * SPU + k2] = make_float2(sg * h.x, sg * h.y);
+    }
+    __syncthreads();
+}
+
+// |L|^2 of the reference's 3x3 "Laplacian" pushed through psf_to_otf: the quadrant assignments broadcast and
+// leave 7 non-zeros:  (0,47)=(1,47)=(46,47)=(47,0)=(47,1)=(47,46)=1, (47,47)=-4.
+__device__ __forceinline__ float lap_quirk_abs2(int k1, int k2, const float2* tw) {
+    const int rr[7] = {0, 1, 46, 47, 47, 47, 47}, cc[7] = {47, 47, 47, 0, 1, 46, 47};
+    const float vv[7] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, -4.f};
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        float2 e = tw[(k1 * rr[i] + k2 * cc[i]) % 48];
+        re += vv[i] * e.x; im += vv[i] * e.y;
+    }
+    return re * re + im * im;
+}
+
+constexpr size_t SOLVER_SMEM = (size_t)(ZU + 2 * SU + 48) * sizeof(float2) + (size_t)2 * NPIX * sizeof(float) + 64;
+
+// kind: GD_SOLVER_* ; one CTA per stamp
+__global__ void __launch_bounds__(U_THREADS) k_solver(int kind, int n_iters, float lam, const float* __restrict__ y,
+                                                      const float* __restrict__ psf, const float* __restrict__ alpha,
+                                                      float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Z = reinterpret_cast<float2*>(smem_raw);
+    float2* S = Z + ZU;
+    float2* SH = S + SU;
+    float2* tw = SH + SU;
+    float* ys = reinterpret_cast<float*>(tw + 48);
+    float* xs = ys + NPIX;
+    const int b = blockIdx.x;
+    const size_t o = (size_t)b * NPIX;
+    fill_twiddles<48>(tw);
+    __syncthreads();
+    otf48(psf + o, Z, SH, tw);
+    const float sc = 1.0f / (48.f * 48.f);
+    if (kind == 0) {                                      // Richardson-Lucy, models/Richard_Lucy.py:10-24
+        // conv_fft_batch(Ht, ones) = conj(H[0,0]) = sum(psf): loop-invariant (:22)
+        const float div = SH[0].x;
+        for (int i = threadIdx.x; i < NPIX; i += blockDim.x) { float v = fmaxf(y[o + i], 0.f); ys[i] = v; xs[i] = v; }
+        __syncthreads();
+        for (int it = 0; it < n_iters; ++it) {
+            for (int i = threadIdx.x; i < ZU; i += blockDim.x) {
+                int j = i / 48, c = i - j * 48;
+                Z[i] = make_float2(xs[(2 * j) * 48 + c], xs[(2 * j + 1) * 48 + c]);
+            }
+            fwd2d<FU48, SPU>(Z, S, tw);
+            for (int q = threadIdx.x; q < FU_SPEC; q += blockDim.x) {
+                int idx = (q / FU_NH) * SPU + (q % FU_NH);
+                S[idx] = cmul(S[idx], SH[idx]);
+            }
+            inv2d<FU48, SPU>(S, Z, tw);                    // Hx (unscaled)
+            for (int i = threadIdx.x; i < ZU; i += blockDim.x) {
+                int j = i / 48, c = i - j * 48;
+                float2 hx = Z[i];
+                Z[i] = make_float2(ys[(2 * j) * 48 + c] / (hx.x * sc), ys[(2 * j + 1) * 48 + c] / (hx.y * sc));   // :21
+            }
+            fwd2d<FU48, SPU>(Z, S, tw);
+            for (int q = threadIdx.x; q < FU_SPEC; q += blockDim.x) {
+                int idx = (q / FU_NH) * SPU + (q % FU_NH);
+                S[idx] = cmul(S[idx], cconj(SH[idx]));
+            }
+            inv2d<FU48, SPU>(S, Z, tw);                    // num (unscaled)
+            for (int i = threadIdx.x; i < ZU; i += blockDim.x) {
+                int j = i / 48, c = i - j * 48;
+                float2 nm = Z[i];
+                int p0 = (2 * j) * 48 + c, p1 = p0 + 48;
+                xs[p0] = xs[p0] * (nm.x * sc) / div;                                                        // :23
+                xs[p1] = xs[p1] * (nm.y * sc) / div;
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < NPIX; i += blockDim.x) out[o + i] = xs[i];
+        return;
+    }
+    const float a = alpha[b];
+    // Wiener: fftn(y) un-clamped, un-scaled (models/Wiener.py:16-18); Tikhonov: fftn(y/alpha) (models/Tikhonet.py:20)
+    load_packed48(Z, y + o, kind == 1 ? 1.f : 1.0f / a, false);
+    fwd2d<FU48, SPU>(Z, S, tw);
+    for (int q = threadIdx.x; q < FU_SPEC; q += blockDim.x) {
+        int s1 = q / FU_NH, k2 = q - s1 * FU_NH, idx = s1 * SPU + k2;
+        float2 h = SH[idx];
+        float hh = h.x * h.x + h.y * h.y;
+        float div = kind == 1 ? hh + 350.f / a
+                  : kind == 2 ? hh + lam
+                              : hh + lam * lap_quirk_abs2(FU48::L::freq(s1), k2, tw);
+        float2 n = cmul(cconj(h), S[idx]);
+        S[idx] = make_float2(n.x / div, n.y / div);
+    }
+    inv2d<FU48, SPU>(S, Z, tw);
+    for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+        int r = i / 48, c = i - r * 48;
+        out[o + i] = zpix<48>(Z, r, c) * sc;
+    }
+}
+
+// conv_fft_batch(H or conj(H), x), utils/utils_torch.py:46-50
+__global__ void __launch_bounds__(U_THREADS) k_conv_fft(const float* __restrict__ x, const float* __restrict__ psf,
+                                                        float* __restrict__ out, int adjoint) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Z = reinterpret_cast<float2*>(smem_raw);
+    float2* S = Z + ZU;
+    float2* SH = S + SU;
+    float2* tw = SH + SU;
+    const size_t o = (size_t)blockIdx.x * NPIX;
+    fill_twiddles<48>(tw);
+    __syncthreads();
+    otf48(psf + o, Z, SH, tw);
+    load_packed48(Z, x + o, 1.f, false);
+    fwd2d<FU48, SPU>(Z, S, tw);
+    for (int q = threadIdx.x; q < FU_SPEC; q += blockDim.x) {
+        int idx = (q / FU_NH) * SPU + (q % FU_NH);
+        S[idx] = cmul(S[idx], adjoint ? cconj(SH[idx]) : SH[idx]);
+    }
+    inv2d<FU48, SPU>(S, Z, tw);
+    for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+        int r = i / 48, c = i - r * 48;
+        out[o + i] = zpix<48>(Z, r, c) * (1.0f / 2304.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Path U.  Per-stamp state in the workspace: H (half spectrum, with the (-1)^k sign), x, z(=denoiser out),
+// v, u1, u2, Hx.  The reference's three conv_fft_batch calls per iteration (:207,:209,:213) collapse to
+// 4 transforms: Hx = F^-1(H X) is produced by the same kernel that produces x.
+// ---------------------------------------------------------------------------------------------------
+constexpr size_t U_SMEM = (size_t)(ZU + 2 * SU + 48) * sizeof(float2) + (size_t)NPIX * sizeof(float) + 64;
+
+// y (clamped, :181), H, rho -> x0 = init_l2 (:170-175), z = x0, v = y or y/alpha, u1 = u2 = 0, Hx0 = conv(H, x0)
+__global__ void __launch_bounds__(U_THREADS) k_u_prologue(const float* __restrict__ y, const float* __restrict__ psf,
+                                                          const float* __restrict__ alpha, int v0_over_alpha,
+                                                          float2* __restrict__ Hw, float* __restrict__ x,
+                                                          float* __restrict__ z, float* __restrict__ v,
+                                                          float* __restrict__ u1, float* __restrict__ u2,
+                                                          float* __restrict__ Hx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Z = reinterpret_cast<float2*>(smem_raw);
+    float2* S = Z + ZU;
+    float2* SH = S + SU;
+    float2* tw = SH + SU;
+    const int b = blockIdx.x;
+    const size_t o = (size_t)b * NPIX;
+    const float a = alpha[b], ia = 1.0f / a;
+    const float sc = 1.0f / 2304.f;
+    fill_twiddles<48>(tw);
+    __syncthreads();
+    otf48(psf + o, Z, SH, tw);
+    float2* Hb = Hw + (size_t)b * FU_SPEC;
+    for (int q = threadIdx.x; q < FU_SPEC; q += blockDim.x) Hb[q] = SH[(q / FU_NH) * SPU + (q % FU_NH)];
+    // init_l2: rhs = fftn(conv_fft_batch(Ht, y/alpha)); the inner conv's ".real" is a no-op on a real signal up to
+    // rounding, so rhs = conj(H) F(y/alpha) without the spatial round trip.
+    load_packed48(Z, y + o, ia, true);
+    fwd2d<FU48, SPU>(Z, S, tw);
+    for (int q = threadIdx.x; q < FU_SPEC; q += blockDim.x) {
+        int idx = (q / FU_NH) * SPU + (q % FU_NH);
+        float2 h = SH[idx];
+        float d = 1.0f / (h.x * h.x + h.y * h.y + ia);
+        float2 n = cmul(cconj(h), S[idx]);
+        S[idx] = make_float2(n.x * d, n.y * d);
+    }
+    inv2d<FU48, SPU>(S, Z, tw);
+    for (int i = threadIdx.x; i < ZU; i += blockDim.x) {
+        int j = i / 48, c = i - j * 48;
+        float2 q = Z[i];
+        q.x = fminf(fmaxf(q.x * sc, 0.f), 1.f);                                                               // :175
+        q.y = fminf(fmaxf(q.y * sc, 0.f), 1.f);
+        Z[i] = q;
+        int p0 = (2 * j) * 48 + c, p1 = p0 + 48;
+        x[o + p0] = q.x; x[o + p1] = q.y;
+        z[o + p0] = q.x; z[o + p1] = q.y;                                                                     // :193
+        float y0 = fmaxf(y[o + p0], 0.f), y1 = fmaxf(y[o + p1], 0.f);
+        v[o + p0] = v0_over_alpha ? y0 * ia : y0;                                                             // :194 / :416
+        v[o + p1] = v0_over_alpha ? y1 * ia : y1;
+        u1[o + p0] = 0.f; u1[o + p1] = 0.f; u2[o + p0] = 0.f; u2[o + p1] = 0.f;
+    }
+    fwd2d<FU48, SPU>(Z, S, tw);
+    for (int q = threadIdx.x; q < FU_SPEC; q += blockDim.x) {
+        int idx = (q / FU_NH) * SPU + (q % FU_NH);
+        S[idx] = cmul(S[idx], SH[idx]);
+    }
+    inv2d<FU48, SPU>(S, Z, tw);
+    for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+        int r = i / 48, c = i - r * 48;
+        Hx[o + i] = zpix<48>(Z, r, c) * sc;
+    }
+}
+
+// elementwise: V-update (:207 with :322-328 / :335-336) and the scaled denoiser input x + u1 (:208)
+__global__ void __launch_bounds__(G_THREADS) k_u_pre(int llh, const float* __restrict__ y, const float* __restrict__ alpha,
+                                                     const float* __restrict__ rho, int n_rho, int n, int it,
+                                                     const float* __restrict__ x, const float* __restrict__ u1,
+                                                     const float* __restrict__ u2, const float* __restrict__ Hx,
+                                                     float* __restrict__ v, float* __restrict__ t,
+                                                     float* __restrict__ tscale) {
+    __shared__ float red[G_THREADS / 32];
+    const int b = blockIdx.x;
+    const size_t o = (size_t)b * NPIX;
+    const float a = alpha[b], rho2 = rho[(size_t)b * n_rho + n + it];
+    float tv[NPIX / G_THREADS], amax = 0.f;
+#pragma unroll
+    for (int e = 0; e < NPIX / G_THREADS; ++e) {
+        size_t i = o + threadIdx.x + e * G_THREADS;
+        float yy = fmaxf(y[i], 0.f);
+        float vt = Hx[i] + u2[i];
+        float vv;
+        if (llh == 1) {
+            float t1 = rho2 * vt - a;
+            vv = 0.5f * (1.0f / rho2) * (-t1 + sqrtf(t1 * t1 + 4.f * yy * rho2));
+        } else {
+            vv = (rho2 * vt + yy / a) / (1.f + rho2);
+        }
+        v[i] = vv;
+        tv[e] = x[i] + u1[i];
+        amax = fmaxf(amax, fabsf(tv[e]));
+    }
+    amax = block_max(amax, red);
+    float inv;
+    float s = pow2_scale(amax, &inv);
+    if (threadIdx.x == 0) tscale[b] = s;
+#pragma unroll
+    for (int e = 0; e < NPIX / G_THREADS; ++e) t[o + threadIdx.x + e * G_THREADS] = tv[e] * inv;
+}
+
+// X-update (:315-319 effective), duals (:212-213); z is the denoiser output of this iteration
+__global__ void __launch_bounds__(U_THREADS) k_u_post(const float2* __restrict__ Hw, const float* __restrict__ rho,
+                                                      int n_rho, int n, int it, const float* __restrict__ z,
+                                                      const float* __restrict__ v, float* __restrict__ x,
+                                                      float* __restrict__ u1, float* __restrict__ u2,
+                                                      float* __restrict__ Hx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Z = reinterpret_cast<float2*>(smem_raw);
+    float2* S = Z + ZU;
+    float2* SB = S + SU;
+    float2* tw = SB + SU;
+    const int b = blockIdx.x;
+    const size_t o = (size_t)b * NPIX;
+    const float rho1 = rho[(size_t)b * n_rho + it], rho2 = rho[(size_t)b * n_rho + n + it];
+    const float sc = 1.0f / 2304.f;
+    const float2* Hb = Hw + (size_t)b * FU_SPEC;
+    fill_twiddles<48>(tw);
+    // A = F(z - u1)
+    for (int i = threadIdx.x; i < ZU; i += blockDim.x) {
+        int j = i / 48, c = i - j * 48;
+        size_t p0 = o + (2 * j) * 48 + c, p1 = p0 + 48;
+        Z[i] = make_float2(z[p0] - u1[p0], z[p1] - u1[p1]);
+    }
+    fwd2d<FU48, SPU>(Z, S, tw);
+    // B = F(v - u2)
+    for (int i = threadIdx.x; i < ZU; i += blockDim.x) {
+        int j = i / 48, c = i - j * 48;
+        size_t p0 = o + (2 * j) * 48 + c, p1 = p0 + 48;
+        Z[i] = make_float2(v[p0] - u2[p0], v[p1] - u2[p1]);
+    }
+    fwd2d<FU48, SPU>(Z, SB, tw);
+    // X = (rho1 A + rho2 conj(H) B) / (rho1 |H|^2 + rho2);  S <- X, SB <- H X
+    for (int q = threadIdx.x; q < FU_SPEC; q += blockDim.x) {
+        int idx = (q / FU_NH) * SPU + (q % FU_NH);
+        float2 h = Hb[q], A = S[idx], Bq = cmul(cconj(h), SB[idx]);
+        float d = 1.0f / (rho1 * (h.x * h.x + h.y * h.y) + rho2);
+        float2 X = make_float2((rho1 * A.x + rho2 * Bq.x) * d, (rho1 * A.y + rho2 * Bq.y) * d);
+        S[idx] = X;
+        SB[idx] = cmul(h, X);
+    }
+    inv2d<FU48, SPU>(S, Z, tw);
+    for (int i = threadIdx.x; i < ZU; i += blockDim.x) {
+        int j = i / 48, c = i - j * 48;
+        size_t p0 = o + (2 * j) * 48 + c, p1 = p0 + 48;
+        float x0 = Z[i].x * sc, x1 = Z[i].y * sc;
+        x[p0] = x0; x[p1] = x1;
+        u1[p0] = u1[p0] + x0 - z[p0];
+        u1[p1] = u1[p1] + x1 - z[p1];
+    }
+    inv2d<FU48, SPU>(SB, Z, tw);
+    for (int i = threadIdx.x; i < ZU; i += blockDim.x) {
+        int j = i / 48, c = i - j * 48;
+        size_t p0 = o + (2 * j) * 48 + c, p1 = p0 + 48;
+        float h0 = Z[i].x * sc, h1 = Z[i].y * sc;
+        Hx[p0] = h0; Hx[p1] = h1;
+        u2[p0] = u2[p0] + h0 - v[p0];
+        u2[p1] = u2[p1] + h1 - v[p1];
+    }
+}
+
+__global__ void k_scale_by_alpha(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ alpha,
+                                 int n, int use_alpha) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = use_alpha ? x[i] * alpha[i / NPIX] : x[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// moment ellipticities (utils/fit_ellipse.py:370-399 normalize_images, :467-548 compute_moments,
+// utils/utils_test.py:92-96): one warp-group per stamp
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(U_THREADS) k_moments(const float* __restrict__ img, float* __restrict__ e12) {
+    __shared__ float red[U_THREADS / 32];
+    const size_t o = (size_t)blockIdx.x * NPIX;
+    float v[U_PER], mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < U_PER; ++e) { v[e] = img[o + threadIdx.x + e * U_THREADS]; mn = fminf(mn, v[e]); mx = fmaxf(mx, v[e]); }
+    mx = block_max(mx, red);
+    mn = -block_max(-mn, red);
+    const float dv = fmaxf(mx - mn, 1e-8f);
+    float m00 = 0.f, sx = 0.f, sy = 0.f;
+#pragma unroll
+    for (int e = 0; e < U_PER; ++e) {
+        int i = threadIdx.x + e * U_THREADS;
+        float g = (v[e] - mn) / dv;
+        v[e] = g;
+        m00 += g; sx += g * (float)(i % 48); sy += g * (float)(i / 48);
+    }
+    m00 = block_sum(m00, red) + 1e-8f;
+    const float cx = block_sum(sx, red) / m00, cy = block_sum(sy, red) / m00;
+    float a20 = 0.f, a11 = 0.f, a02 = 0.f;
+#pragma unroll
+    for (int e = 0; e < U_PER; ++e) {
+        int i = threadIdx.x + e * U_THREADS;
+        float dx = (float)(i % 48) - cx, dy = (float)(i / 48) - cy;
+        a20 += v[e] * dx * dx; a11 += v[e] * dx * dy; a02 += v[e] * dy * dy;
+    }
+    const float mu20 = block_sum(a20, red) / m00, mu11 = block_sum(a11, red) / m00, mu02 = block_sum(a02, red) / m00;
+    if (threadIdx.x == 0) {
+        e12[2 * blockIdx.x] = (mu20 - mu02) / (mu20 + mu02);
+        e12[2 * blockIdx.x + 1] = 2.f * mu11 / (mu20 + mu02);
+    }
+}
+
+// =====================================================================================================
+// host launchers
+// =====================================================================================================
+template <class K> static int opt_in_smem(K kernel, size_t bytes) {
+    GD_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return GD_OK;
+}
+
+int fft_kernels_init() {
+    int rc;
+    if ((rc = opt_in_smem(k_g_prologue, G_SMEM_PRO))) return rc;
+    if ((rc = opt_in_smem(k_g_xupdate, G_SMEM_XUP))) return rc;
+    if ((rc = opt_in_smem(k_solver, SOLVER_SMEM))) return rc;
+    if ((rc = opt_in_smem(k_conv_fft, SOLVER_SMEM))) return rc;
+    if ((rc = opt_in_smem(k_u_prologue, U_SMEM))) return rc;
+    if ((rc = opt_in_smem(k_u_post, U_SMEM))) return rc;
+    return GD_OK;
+}
+
+int launch_g_prologue(const float* y, const float* psf, const float* alpha, float2* Pc, float* HtH, float* z, float* u,
+                      float* x, int batch, cudaStream_t st) {
+    if (batch <= 0) return GD_OK;
+    k_g_prologue<<<batch, G_THREADS, G_SMEM_PRO, st>>>(y, psf, alpha, Pc, HtH, z, u, x);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_g_xupdate(const float2* Pc, const float* HtH, const float* rho, int n_rho, int it, const float* z, float* x,
+                     float* u, float* t, float* tscale, int batch, cudaStream_t st) {
+    if (batch <= 0) return GD_OK;
+    k_g_xupdate<<<batch, G_THREADS, G_SMEM_XUP, st>>>(Pc, HtH, rho, n_rho, it, z, x, u, t, tscale);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_g_dual_out(const float* rho, int n_rho, int it, const float* x, const float* z, const float* u, float* uo,
+                      int batch, cudaStream_t st) {
+    int n = batch * NPIX;
+    if (n <= 0) return GD_OK;
+    k_g_dual_out<<<(n + 255) / 256, 256, 0, st>>>(rho, n_rho, it, x, z, u, uo, n);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_scale_in(const float* in, float* t, float* tscale, int batch, cudaStream_t st) {
+    if (batch <= 0) return GD_OK;
+    k_scale_in<<<batch, G_THREADS, 0, st>>>(in, t, tscale);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_fill_rho(const float* src, int n_rho, float* rho, int batch, cudaStream_t st) {
+    int n = batch * n_rho;
+    if (n <= 0) return GD_OK;
+    k_fill_rho<<<(n + 255) / 256, 256, 0, st>>>(src, n_rho, rho, batch);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_solver(int kind, int n_iters, float lam, const float* y, const float* psf, const float* alpha, float* out,
+                  int batch, cudaStream_t st) {
+    if (batch <= 0) return GD_OK;
+    k_solver<<<batch, U_THREADS, SOLVER_SMEM, st>>>(kind, n_iters, lam, y, psf, alpha, out);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_conv_fft(const float* x, const float* psf, float* out, int adjoint, int batch, cudaStream_t st) {
+    if (batch <= 0) return GD_OK;
+    k_conv_fft<<<batch, U_THREADS, SOLVER_SMEM, st>>>(x, psf, out, adjoint);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_u_prologue(const float* y, const float* psf, const float* alpha, int v0_over_alpha, float2* Hw, float* x,
+                      float* z, float* v, float* u1, float* u2, float* Hx, int batch, cudaStream_t st) {
+    if (batch <= 0) return GD_OK;
+    k_u_prologue<<<batch, U_THREADS, U_SMEM, st>>>(y, psf, alpha, v0_over_alpha, Hw, x, z, v, u1, u2, Hx);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_u_pre(int llh, const float* y, const float* alpha, const float* rho, int n_rho, int n, int it, const float* x,
+                 const float* u1, const float* u2, const float* Hx, float* v, float* t, float* tscale, int batch,
+                 cudaStream_t st) {
+    if (batch <= 0) return GD_OK;
+    k_u_pre<<<batch, G_THREADS, 0, st>>>(llh, y, alpha, rho, n_rho, n, it, x, u1, u2, Hx, v, t, tscale);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_u_post(const float2* Hw, const float* rho, int n_rho, int n, int it, const float* z, const float* v, float* x,
+                  float* u1, float* u2, float* Hx, int batch, cudaStream_t st) {
+    if (batch <= 0) return GD_OK;
+    k_u_post<<<batch, U_THREADS, U_SMEM, st>>>(Hw, rho, n_rho, n, it, z, v, x, u1, u2, Hx);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_scale_by_alpha(float* out, const float* x, const float* alpha, int batch, int use_alpha, cudaStream_t st) {
+    int n = batch * NPIX;
+    if (n <= 0) return GD_OK;
+    k_scale_by_alpha<<<(n + 255) / 256, 256, 0, st>>>(out, x, alpha, n, use_alpha);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_moments(const float* img, float* e12, int batch, cudaStream_t st) {
+    if (batch <= 0) return GD_OK;
+    k_moments<<<batch, U_THREADS, 0, st>>>(img, e12);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+
+}  // namespace gd

@@ -1,0 +1,97 @@
+// Shared definitions for libgdeconv (B200 / sm_100a): activation layouts, layer parameter blocks,
+// error plumbing.  See DESIGN.md for the data layout in HBM.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gdeconv.h"
+
+#ifndef GD_HD
+#define GD_HD __host__ __device__ __forceinline__
+#endif
+
+namespace gd {
+
+constexpr int STAMP = 48;
+constexpr int NPIX = STAMP * STAMP;          // 2304
+constexpr int FG = 96;                       // zero-padded grid of path G (pad_double, utils_torch.py:11-13)
+constexpr int FG_NH = FG / 2 + 1;            // 49
+constexpr int FG_SPEC = FG * FG_NH;          // half-spectrum elements per stamp (digit-swapped k1, natural k2)
+constexpr int FU_NH = STAMP / 2 + 1;         // 25
+constexpr int FU_SPEC = STAMP * FU_NH;       // 48x25 half spectrum of the circular 48x48 transforms
+constexpr int MTILE = 128;                   // GEMM rows (pixels) per tile = tcgen05 M
+
+enum Precision { PREC_FP32_SIMT = GD_PREC_FP32_SIMT, PREC_FP16_UMMA = GD_PREC_FP16_UMMA, PREC_FP16_SIMT = GD_PREC_FP16_SIMT };
+
+// ---------------------------------------------------------------------------------------------------
+// Activation layout ("padded-linear, channel-chunk-major").
+//
+// A feature map of C channels at resolution HxW for a chunk of B stamps is stored as
+//     act[C / CH][Ptot][CH]          CH = 8 for fp16, 4 for fp32  (one 16-byte vector per pixel and chunk)
+// where the pixel axis is a single linear index
+//     row(b, y, x) = base0 + b*S + y*Wp + x,   Wp = W+1,  S = (H+1)*Wp,  base0 = Wp+1
+// i.e. every image row is followed by ONE zero pixel and every stamp by ONE zero row; those zeros are shared
+// by the neighbours on both sides, so the 3x3 tap (dy,dx) of ANY pixel is simply row + dy*Wp + dx and a conv
+// is a GEMM whose A operand for tap t is the same buffer shifted by a constant number of 16-byte rows.
+// Halo rows are never written (the buffer is zeroed once per forward), the GEMM computes garbage there and
+// the epilogue drops it.  Overhead (H+1)(W+1)/(HW): 4 % at 48x48 ... 36 % at 6x6.
+// ---------------------------------------------------------------------------------------------------
+struct Geom {
+    int H, W, Wp, S, base0, Ptot, M;          // M = B*S GEMM rows to compute
+};
+
+inline Geom make_geom(int H, int batch) {
+    Geom g;
+    g.H = H; g.W = H; g.Wp = H + 1; g.S = (H + 1) * (H + 1); g.base0 = g.Wp + 1;
+    g.M = batch * g.S;
+    int mt = ((g.M + MTILE - 1) / MTILE + 7) / 8 * 8;
+    // a CTA of the tcgen05 kernel owns up to 8 consecutive tiles and its window reaches Wp+1 rows past them
+    g.Ptot = mt * MTILE + 2 * g.base0 + MTILE;
+    return g;
+}
+
+GD_HD bool row_valid(int m, int S, int Wp, int H, int W, int M) {
+    if (m >= M) return false;
+    int r = m % S;
+    return (r / Wp) < H && (r % Wp) < W;
+}
+
+// One conv / strided-conv / transposed-conv layer as a GEMM over taps (all layers of models/ResUNet.py:11-24
+// except head and tail).  D[m, n] = sum_t sum_k A[m + off[t], t*? ...] -- see conv_simt.cu / conv_umma.cu.
+struct ConvParams {
+    Geom g;                   // geometry of the GEMM rows (level the accumulators live on)
+    int ntaps;                // 9 (3x3) or 1 (k2s2 down on space-to-depth input, k2s2 up)
+    int off[9];               // row offset per tap
+    int Kt;                   // input channels per tap
+    int N;                    // GEMM N (C_out, or 4*C_out for the transposed conv)
+    const void* a;            // input activations  [Kt/CH][g.Ptot][CH]
+    const void* w;            // weights, layout depends on the kernel (see pack.cu)
+    int relu;
+    // epilogue, all optional.  mode 0: outputs live on the GEMM-row level (C = N, Ptot = g.Ptot).
+    const float* res32;       // += residual (fp32 stream)
+    const float* skip32;      // += U-Net skip (fp32)
+    float* out32;             // fp32 result [N/4][Ptot][4]
+    void* out16;              // operand-precision copy for the next conv [N/CH][Ptot][CH]
+    void* s2d;                // space-to-depth copy for the following k2s2 strided conv, coarse geometry gc
+    // mode 1 (transposed conv): column n = tap*Cf + c scatters to fine pixel (2Y+dy, 2X+dx), geometry gf
+    int mode;
+    int Cf;
+    Geom gc;                  // coarse level (s2d target)
+    Geom gf;                  // fine level (mode 1 target)
+};
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing (C ABI returns ints; message retrievable through gd_last_error())
+// ---------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define GD_CUDA_CHECK(expr)                                                                         \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            gd::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return GD_ECUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+}  // namespace gd

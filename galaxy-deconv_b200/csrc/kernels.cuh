@@ -1,0 +1,41 @@
+// Host-callable launchers of every kernel in libgdeconv (definitions in fft_kernels.cu, subnet.cu, conv_simt.cu,
+// conv_umma.cu).  All are stream-ordered and return GD_OK or a negative GD_E* code.
+#pragma once
+#include "gd_common.cuh"
+#include "subnet.cuh"
+
+namespace gd {
+
+int fft_kernels_init();
+int subnet_init();
+int conv_umma_init();
+
+int launch_g_prologue(const float* y, const float* psf, const float* alpha, float2* Pc, float* HtH, float* z, float* u,
+                      float* x, int batch, cudaStream_t st);
+int launch_g_xupdate(const float2* Pc, const float* HtH, const float* rho, int n_rho, int it, const float* z, float* x,
+                     float* u, float* t, float* tscale, int batch, cudaStream_t st);
+int launch_g_dual_out(const float* rho, int n_rho, int it, const float* x, const float* z, const float* u, float* uo,
+                      int batch, cudaStream_t st);
+int launch_scale_in(const float* in, float* t, float* tscale, int batch, cudaStream_t st);
+int launch_fill_rho(const float* src, int n_rho, float* rho, int batch, cudaStream_t st);
+int launch_solver(int kind, int n_iters, float lam, const float* y, const float* psf, const float* alpha, float* out,
+                  int batch, cudaStream_t st);
+int launch_conv_fft(const float* x, const float* psf, float* out, int adjoint, int batch, cudaStream_t st);
+int launch_u_prologue(const float* y, const float* psf, const float* alpha, int v0_over_alpha, float2* Hw, float* x,
+                      float* z, float* v, float* u1, float* u2, float* Hx, int batch, cudaStream_t st);
+int launch_u_pre(int llh, const float* y, const float* alpha, const float* rho, int n_rho, int n, int it, const float* x,
+                 const float* u1, const float* u2, const float* Hx, float* v, float* t, float* tscale, int batch,
+                 cudaStream_t st);
+int launch_u_post(const float2* Hw, const float* rho, int n_rho, int n, int it, const float* z, const float* v, float* x,
+                  float* u1, float* u2, float* Hx, int batch, cudaStream_t st);
+int launch_scale_by_alpha(float* out, const float* x, const float* alpha, int batch, int use_alpha, cudaStream_t st);
+int launch_moments(const float* img, float* e12, int batch, cudaStream_t st);
+int launch_subnet(const SubnetParams& P, const float* psf, const float* alpha, float* rho, int batch, cudaStream_t st);
+
+int launch_conv_simt(const ConvParams& p, int prec, cudaStream_t st);
+int launch_conv_umma(const ConvParams& p, cudaStream_t st);
+int launch_head(const float* t, const float* w, int C0, const ConvParams& p, int batch, int prec, cudaStream_t st);
+int launch_tail(const float* x32, const float* w, int C0, const Geom& g, const float* tscale, float* z, int batch,
+                cudaStream_t st);
+
+}  // namespace gd
