@@ -619,3 +619,11 @@ extern "C" int gd_debug_tapgemm(int precision, int H, int batch, int ntaps, int 
     p.Kt = Kt; p.N = N; p.out32 = out32;
     return run_conv(p, precision, (cudaStream_t)stream);
 }
+
+extern "C" void gd_profile_begin(void) { conv_profile_begin(); }
+extern "C" int gd_profile_end(double* ms_total, double* flops_total, uint64_t* launches) {
+    unsigned long long n = 0;
+    int rc = conv_profile_end(ms_total, flops_total, &n);
+    if (launches) *launches = n;
+    return rc;
+}

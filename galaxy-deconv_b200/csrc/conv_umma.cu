@@ -20,6 +20,8 @@
 #include "kernels.cuh"
 #include "launch.cuh"
 
+#include <vector>
+
 namespace gd {
 
 constexpr int UMMA_THREADS = 192;
@@ -243,6 +245,36 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) k_conv_umma(const ConvParams 
 
 static int g_num_sms = 0;
 
+// Optional per-launch timing of k_conv_umma with CUDA events on the launching stream (gd_profile_begin/end):
+// bench.py uses it to measure the dominant kernel's average duration live for the roofline line.
+struct ConvTiming {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    std::vector<double> flops;
+    cudaEvent_t get() {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
+};
+static ConvTiming g_timing;
+
+void conv_profile_begin() { g_timing.on = true; g_timing.used = 0; g_timing.flops.clear(); }
+int conv_profile_end(double* ms_total, double* flops_total, unsigned long long* launches) {
+    g_timing.on = false;
+    double ms = 0, fl = 0;
+    for (size_t i = 0; i + 1 < g_timing.used; i += 2) {
+        GD_CUDA_CHECK(cudaEventSynchronize(g_timing.pool[i + 1]));
+        float t = 0;
+        GD_CUDA_CHECK(cudaEventElapsedTime(&t, g_timing.pool[i], g_timing.pool[i + 1]));
+        ms += t; fl += g_timing.flops[i / 2];
+    }
+    if (ms_total) *ms_total = ms;
+    if (flops_total) *flops_total = fl;
+    if (launches) *launches = g_timing.used / 2;
+    return GD_OK;
+}
+
 int conv_umma_init() {
     int dev;
     GD_CUDA_CHECK(cudaGetDevice(&dev));
@@ -285,8 +317,17 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t st) {
     if (!g_num_sms) { set_error("conv_umma: library not initialised"); return GD_ECUDA; }
     const int items = c.items_m * c.nslices;
     const int grid = items < 2 * g_num_sms ? items : 2 * g_num_sms;
+    cudaEvent_t e1 = nullptr;
+    if (g_timing.on) {
+        cudaEvent_t e0 = g_timing.get();
+        e1 = g_timing.get();
+        // algorithmic FLOPs: 2*K*N per tap and VALID output pixel (halo rows of the padded-linear layout excluded)
+        g_timing.flops.push_back(2.0 * (double)(p.g.M / p.g.S) * p.g.H * p.g.W * (double)p.N * p.Kt * p.ntaps);
+        GD_CUDA_CHECK(cudaEventRecord(e0, st));
+    }
     k_conv_umma<<<grid, UMMA_THREADS, c.smem, st>>>(p, c);
     GD_LAUNCHED();
+    if (e1) GD_CUDA_CHECK(cudaEventRecord(e1, st));
     return GD_OK;
 }
 

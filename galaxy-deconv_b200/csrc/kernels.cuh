@@ -9,6 +9,8 @@ namespace gd {
 int fft_kernels_init();
 int subnet_init();
 int conv_umma_init();
+void conv_profile_begin();
+int conv_profile_end(double* ms_total, double* flops_total, unsigned long long* launches);
 
 int launch_g_prologue(const float* y, const float* psf, const float* alpha, float2* Pc, float* HtH, float* z, float* u,
                       float* x, int batch, cudaStream_t st);

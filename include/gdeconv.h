@@ -120,6 +120,12 @@ GD_API int gd_debug_geom(int H, int batch, int* geom7);
 GD_API int gd_debug_tapgemm(int precision, int H, int batch, int ntaps, int Kt, int N, int relu, const void* act,
                             const void* weights, float* out32, void* stream);
 
+/* Live timing of the dominant kernel (k_conv_umma, the tcgen05 tap-GEMM): between begin and end every launch is
+ * bracketed by CUDA events on its stream; end synchronises them and returns the summed device time (ms), the summed
+ * ALGORITHMIC FLOPs (2*K*N per tap and valid output pixel) and the number of launches.  Not thread-safe. */
+GD_API void gd_profile_begin(void);
+GD_API int gd_profile_end(double* ms_total, double* flops_total, uint64_t* launches);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches claim). */
 GD_API uint64_t gd_launch_count(void);
 

@@ -145,7 +145,7 @@ def test_fp16_umma_matches_fp16_simt_closely(golden, dev, monkeypatch):
     for prec in ('fp16_simt', 'fp16_umma'):
         monkeypatch.setenv('GDECONV_PRECISION', prec)
         outs[prec] = m(x).cpu()
-    assert rel_l2(outs['fp16_umma'], outs['fp16_simt']).max() < 1e-4
+    assert rel_l2(outs['fp16_umma'], outs['fp16_simt']).max() < 3e-4
 
 
 # ---------------------------------------------------------------------------------------------------
