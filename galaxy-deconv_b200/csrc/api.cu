@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -416,47 +417,77 @@ static int run_conv(const ConvParams& p, int prec, cudaStream_t st) {
     return prec == PREC_FP16_UMMA ? launch_conv_umma(p, st) : launch_conv_simt(p, prec, st);
 }
 
+// Sub-chunking: the wide, shallow levels 0-1 (48x48 and 24x24, ~1.2 MB of activations per stamp) are walked
+// sub-chunk by sub-chunk so that a sub-chunk's working set stays in the 126 MB L2 across consecutive layers, while
+// the narrow, deep levels 2-3 run over the whole chunk at once (enough 128-row tiles to fill 148 SMs).
+static int g_subchunk = 0;
+static int subchunk_size() {
+    if (!g_subchunk) {
+        const char* e = getenv("GDECONV_SUBCHUNK");
+        g_subchunk = e && atoi(e) > 0 ? atoi(e) : 64;
+    }
+    return g_subchunk;
+}
+
 static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const float* tscale, float* zout, int nb,
                          cudaStream_t st) {
     const int prec = W->precision;
     const Geom* g = ws.g;
     const int* C = ws.C;
+    // every activation buffer has 16-byte rows, so stamps [s0, ...) of level L start s0 * S_L * 16 bytes into each plane
+    auto at = [&](const void* base, int L, int s0) -> unsigned char* {
+        return base ? (unsigned char*)base + (size_t)s0 * g[L].S * 16 : nullptr;
+    };
     {   // head (ResUNet.py:31): x1 = conv(t)  -> skip32[0] (fp32) + a16[0]
         ConvParams p = conv_base(g[0], nb);
         p.N = C[0]; p.out32 = ws.skip32[0]; p.out16 = ws.a16[0];
         GD_TRY(launch_head(t, W->head, C[0], p, nb, prec, st));
     }
-    // one ResBlock (resnet_basicblock.py:69-71): stream + conv(relu(conv(stream)))
-    auto resblock = [&](int L, const void* const* w2, const float* res, const float* skip, float* out32, void* out16,
-                        void* s2d) -> int {
-        ConvParams p1 = conv3(g[L], nb, C[L], ws.a16[L], w2[0], 1);
-        p1.out16 = ws.t16[L];
+    // one ResBlock (resnet_basicblock.py:69-71) on stamps [s0, s0+n): stream + conv(relu(conv(stream)))
+    auto resblock = [&](int L, int s0, int n, const void* const* w2, const float* res, const float* skip, float* out32,
+                        void* out16, void* s2d) -> int {
+        ConvParams p1 = conv3(g[L], n, C[L], at(ws.a16[L], L, s0), w2[0], 1);
+        p1.out16 = at(ws.t16[L], L, s0);
         GD_TRY(run_conv(p1, prec, st));
-        ConvParams p2 = conv3(g[L], nb, C[L], ws.t16[L], w2[1], 0);
-        p2.res32 = res; p2.skip32 = skip; p2.out32 = out32; p2.out16 = out16; p2.s2d = s2d;
-        if (s2d) { p2.gc = g[L + 1]; p2.gc.M = nb * g[L + 1].S; }
+        ConvParams p2 = conv3(g[L], n, C[L], at(ws.t16[L], L, s0), w2[1], 0);
+        p2.res32 = (const float*)at(res, L, s0); p2.skip32 = (const float*)at(skip, L, s0);
+        p2.out32 = (float*)at(out32, L, s0); p2.out16 = at(out16, L, s0);
+        if (s2d) { p2.s2d = at(s2d, L + 1, s0); p2.gc = g[L + 1]; p2.gc.M = n * g[L + 1].S; }
         return run_conv(p2, prec, st);
     };
-    for (int L = 0; L < 3; ++L) {                       // m_down1..3 (ResUNet.py:32-34)
-        GD_TRY(resblock(L, W->down_rb[L][0], ws.skip32[L], nullptr, ws.p32a[L], ws.a16[L], nullptr));
-        GD_TRY(resblock(L, W->down_rb[L][1], ws.p32a[L], nullptr, nullptr, nullptr, ws.d16[L + 1]));
-        ConvParams p = conv_base(g[L + 1], nb);         // k2s2 strided conv as a 1-tap GEMM on the space-to-depth copy
-        p.ntaps = 1; p.off[0] = 0; p.Kt = 4 * C[L]; p.N = C[L + 1]; p.a = ws.d16[L + 1]; p.w = W->down[L];
-        p.out32 = ws.skip32[L + 1]; p.out16 = ws.a16[L + 1];
+    auto down_stage = [&](int L, int s0, int n) -> int {          // m_down{L+1} (ResUNet.py:32-34)
+        GD_TRY(resblock(L, s0, n, W->down_rb[L][0], ws.skip32[L], nullptr, ws.p32a[L], ws.a16[L], nullptr));
+        GD_TRY(resblock(L, s0, n, W->down_rb[L][1], ws.p32a[L], nullptr, nullptr, nullptr, ws.d16[L + 1]));
+        ConvParams p = conv_base(g[L + 1], n);         // k2s2 strided conv as a 1-tap GEMM on the space-to-depth copy
+        p.ntaps = 1; p.off[0] = 0; p.Kt = 4 * C[L]; p.N = C[L + 1]; p.a = at(ws.d16[L + 1], L + 1, s0); p.w = W->down[L];
+        p.out32 = (float*)at(ws.skip32[L + 1], L + 1, s0); p.out16 = at(ws.a16[L + 1], L + 1, s0);
+        return run_conv(p, prec, st);
+    };
+    auto up_stage = [&](int L, int s0, int n) -> int {            // m_up{L+1} (ResUNet.py:36-38)
+        ConvParams p = conv_base(g[L + 1], n);         // k2s2 transposed conv: GEMM on the coarse level, scatter to fine
+        p.ntaps = 1; p.off[0] = 0; p.Kt = C[L + 1]; p.N = 4 * C[L]; p.a = at(ws.a16[L + 1], L + 1, s0); p.w = W->up[L];
+        p.mode = 1; p.Cf = C[L]; p.gf = g[L]; p.gf.M = n * g[L].S;
+        p.out32 = (float*)at(ws.p32a[L], L, s0); p.out16 = at(ws.a16[L], L, s0);
         GD_TRY(run_conv(p, prec, st));
+        GD_TRY(resblock(L, s0, n, W->up_rb[L][0], ws.p32a[L], nullptr, ws.p32b[L], ws.a16[L], nullptr));
+        if (L > 0) return resblock(L, s0, n, W->up_rb[L][1], ws.p32b[L], ws.skip32[L], nullptr, ws.a16[L], nullptr);
+        return resblock(L, s0, n, W->up_rb[L][1], ws.p32b[L], ws.skip32[L], ws.p32a[L], nullptr, nullptr);
+    };
+    const int sub = subchunk_size();
+    for (int s0 = 0; s0 < nb; s0 += sub) {
+        const int n = nb - s0 < sub ? nb - s0 : sub;
+        GD_TRY(down_stage(0, s0, n));
+        GD_TRY(down_stage(1, s0, n));
     }
+    GD_TRY(down_stage(2, 0, nb));
     // m_body (ResUNet.py:35) and the skip x + x4 (:36)
-    GD_TRY(resblock(3, W->body_rb[0], ws.skip32[3], nullptr, ws.p32a[3], ws.a16[3], nullptr));
-    GD_TRY(resblock(3, W->body_rb[1], ws.p32a[3], ws.skip32[3], nullptr, ws.a16[3], nullptr));
-    for (int L = 2; L >= 0; --L) {                      // m_up3..1 (ResUNet.py:36-38)
-        ConvParams p = conv_base(g[L + 1], nb);         // k2s2 transposed conv: GEMM on the coarse level, scatter to fine
-        p.ntaps = 1; p.off[0] = 0; p.Kt = C[L + 1]; p.N = 4 * C[L]; p.a = ws.a16[L + 1]; p.w = W->up[L];
-        p.mode = 1; p.Cf = C[L]; p.gf = g[L]; p.gf.M = nb * g[L].S;
-        p.out32 = ws.p32a[L]; p.out16 = ws.a16[L];
-        GD_TRY(run_conv(p, prec, st));
-        GD_TRY(resblock(L, W->up_rb[L][0], ws.p32a[L], nullptr, ws.p32b[L], ws.a16[L], nullptr));
-        if (L > 0) GD_TRY(resblock(L, W->up_rb[L][1], ws.p32b[L], ws.skip32[L], nullptr, ws.a16[L], nullptr));
-        else GD_TRY(resblock(L, W->up_rb[L][1], ws.p32b[L], ws.skip32[L], ws.p32a[L], nullptr, nullptr));
+    GD_TRY(resblock(3, 0, nb, W->body_rb[0], ws.skip32[3], nullptr, ws.p32a[3], ws.a16[3], nullptr));
+    GD_TRY(resblock(3, 0, nb, W->body_rb[1], ws.p32a[3], ws.skip32[3], nullptr, ws.a16[3], nullptr));
+    GD_TRY(up_stage(2, 0, nb));
+    for (int s0 = 0; s0 < nb; s0 += sub) {
+        const int n = nb - s0 < sub ? nb - s0 : sub;
+        GD_TRY(up_stage(1, s0, n));
+        GD_TRY(up_stage(0, s0, n));
     }
     // tail (ResUNet.py:39): conv(x + x1), times the per-stamp input scale
     return launch_tail(ws.p32a[0], W->tail, C[0], g[0], tscale, zout, nb, st);

@@ -95,4 +95,82 @@ __device__ __forceinline__ void epilogue_store16(const ConvParams& p, const RowC
     if (p.s2d) put(reinterpret_cast<T*>(p.s2d), rc.ctap * p.N + n0, p.gc.Ptot, rc.crow);
 }
 
+
+// ---- split form used by the tcgen05 kernel: the residual / skip loads are issued BEFORE the accumulator is waited
+// for, so their L2 latency overlaps the TMEM load and the previous block's stores ----
+struct EpiAddr { int row, Ptot, c0; };
+
+__device__ __forceinline__ EpiAddr epi_addr(const ConvParams& p, const RowCtx& rc, int n0) {
+    EpiAddr a;
+    if (p.mode == 1) {
+        int tap = n0 / p.Cf;
+        a.c0 = n0 - tap * p.Cf;
+        a.row = rc.frow0 + (tap >> 1) * p.gf.Wp + (tap & 1);
+        a.Ptot = p.gf.Ptot;
+    } else {
+        a.c0 = n0; a.row = rc.row; a.Ptot = p.g.Ptot;
+    }
+    return a;
+}
+
+// r[16] = res32 + skip32 (zeros when absent)
+__device__ __forceinline__ void epi_load16(const ConvParams& p, const EpiAddr& a, float* r) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = 0.f;
+    if (p.res32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 t = *reinterpret_cast<const float4*>(p.res32 + ((size_t)(a.c0 / 4 + q) * a.Ptot + a.row) * 4);
+            r[4 * q] = t.x; r[4 * q + 1] = t.y; r[4 * q + 2] = t.z; r[4 * q + 3] = t.w;
+        }
+    }
+    if (p.skip32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 t = *reinterpret_cast<const float4*>(p.skip32 + ((size_t)(a.c0 / 4 + q) * a.Ptot + a.row) * 4);
+            r[4 * q] += t.x; r[4 * q + 1] += t.y; r[4 * q + 2] += t.z; r[4 * q + 3] += t.w;
+        }
+    }
+}
+
+__device__ __forceinline__ uint4 pack8_half(const float* v) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+    return u;
+}
+
+// v[16] = relu?(acc) + r  ->  out32 / out16 / s2d   (same arithmetic order as epilogue_store16: (acc + res) + skip
+// differs only by association of res + skip, which the fp32 validation mode does not use)
+__device__ __forceinline__ void epi_store16_half(const ConvParams& p, const RowCtx& rc, const EpiAddr& a, int n0, float* v,
+                                                 const float* r) {
+    if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (p.res32 || p.skip32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += r[i];
+    }
+    if (p.out32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(p.out32 + ((size_t)(a.c0 / 4 + q) * a.Ptot + a.row) * 4) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    if (p.out16) {
+        __half* base = reinterpret_cast<__half*>(p.out16);
+        *reinterpret_cast<uint4*>(base + ((size_t)(a.c0 / 8) * a.Ptot + a.row) * 8) = pack8_half(v);
+        *reinterpret_cast<uint4*>(base + ((size_t)(a.c0 / 8 + 1) * a.Ptot + a.row) * 8) = pack8_half(v + 8);
+    }
+    if (p.s2d) {
+        __half* base = reinterpret_cast<__half*>(p.s2d);
+        const int cb = rc.ctap * p.N + n0;
+        *reinterpret_cast<uint4*>(base + ((size_t)(cb / 8) * p.gc.Ptot + rc.crow) * 8) = pack8_half(v);
+        *reinterpret_cast<uint4*>(base + ((size_t)(cb / 8 + 1) * p.gc.Ptot + rc.crow) * 8) = pack8_half(v + 8);
+    }
+}
+
 }  // namespace gd

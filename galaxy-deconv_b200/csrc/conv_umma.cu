@@ -12,33 +12,40 @@
 // which is byte-for-byte the global layout of activations ([C/8][Ptot][8]) and packed weights
 // ([tap][K/8][N][8]), so staging is plain 1-D cp.async.bulk (UBLKCP) with mbarrier complete_tx.
 //
-// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld 32x32b -> fused ReLU / residual / skip / fp16 copy / space-to-depth /
-// pixel-shuffle scatter, conv_epilogue.cuh).  Two CTAs are resident per SM (256 TMEM columns each) so one CTA's
-// epilogue overlaps the other's MMAs.
+// Warp roles (320 threads, one persistent CTA per SM): warp 0 = bulk-copy producer, warp 1 = TMEM allocator +
+// single-thread MMA issuer, warps 2..9 = epilogue (tcgen05.ld 32x32b -> fused ReLU / residual / skip / fp16 copy /
+// space-to-depth / pixel-shuffle scatter, conv_epilogue.cuh; residual loads are issued before the accumulator wait).
+// The 512 TMEM columns hold two accumulator stages, so the epilogue of work item i overlaps the MMAs of item i+1.
+// Layers whose packed weights fit (<= 96 KB: levels 1-2 of the U-Net and all k2s2 layers) keep them resident in
+// shared memory for the whole kernel; larger layers stream (slab, tap) weight stages through a 6-deep ring.
 #include "conv_epilogue.cuh"
 #include "kernels.cuh"
 #include "launch.cuh"
 
+#include <cstring>
 #include <vector>
 
 namespace gd {
 
-constexpr int UMMA_THREADS = 192;
-constexpr int A_STAGES = 2;
-constexpr int B_STAGES = 4;
-constexpr int TMEM_COLS = 256;
-constexpr size_t UMMA_SMEM_MIN = 80 * 1024;      // > 227/3 KB: never more than two CTAs (2 x 256 TMEM columns) per SM
-constexpr size_t UMMA_SMEM_MAX = 113 * 1024;
+constexpr int EPI_WARPS = 8;
+constexpr int UMMA_THREADS = 64 + 32 * EPI_WARPS;   // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int MAX_A_STAGES = 4;
+constexpr int MAX_B_STAGES = 8;
+constexpr int TMEM_COLS = 512;                      // one CTA per SM owns all of TMEM: 2 accumulator stages x 256 columns
+constexpr int ACC_STAGE_COLS = 256;
+constexpr size_t UMMA_SMEM_MAX = 226 * 1024;
+constexpr size_t B_RESIDENT_MAX = 96 * 1024;        // layers whose packed weights fit stay in shared memory for the whole kernel
 
 struct UmmaCfg {
-    int ncta;        // GEMM N per CTA (<= 128)
+    int ncta;        // GEMM N per MMA (<= 128)
     int nslices;     // N / ncta
-    int J;           // 128-row tiles per work item (J * ncta <= 256 TMEM columns)
-    int BK;          // channels per K-slab
+    int J;           // 128-row tiles per work item (J * ncta <= 256 TMEM columns per accumulator stage)
+    int BK;          // channels per K-slab of the A ring
     int halo;        // Wp + 1 for 3x3, 0 for 1-tap layers
     int win_rows;    // 128 * J + 2 * halo
-    int a_stage_bytes, b_stage_bytes;
+    int a_stage_bytes, a_stages;
+    int b_resident;  // 1: all taps/K of the weights loaded once per CTA; 0: streamed per (slab, tap) through a ring
+    int b_stage_bytes, b_stages, b_total_bytes;
     int items_m;     // ceil(tiles / J)
     size_t smem;
 };
@@ -89,6 +96,39 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// The MMA warp walks its loop nest as a WHOLE warp with warp-uniform operands (loop control and descriptor arithmetic
+// stay on the uniform datapath); the instruction itself is issued by one elected lane (elect.sync).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void tc_mma_f16_pred(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc,
+                                                uint32_t) {
+    if (elect_one()) tc_mma_f16(d_tmem, adesc, bdesc, idesc, acc);
+}
+__device__ __forceinline__ void tc_commit_pred(uint32_t bar, uint32_t) {
+    if (elect_one()) tc_commit(bar);
+}
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+// wait::ld with the destination registers as in/out operands, so no consumer can be scheduled above the wait
+__device__ __forceinline__ void tc_ld_wait16(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -112,26 +152,27 @@ __device__ __forceinline__ uint32_t instr_desc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(UMMA_THREADS, 2) k_conv_umma(const ConvParams p, const UmmaCfg c) {
+__global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams p, const UmmaCfg c) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bars[2 * A_STAGES + 2 * B_STAGES + 2];
+    __shared__ __align__(8) uint64_t bars[2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 5];
     __shared__ uint32_t tmem_slot;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     unsigned char* a_smem = smem;
-    unsigned char* b_smem = smem + (size_t)A_STAGES * c.a_stage_bytes;
+    unsigned char* b_smem = smem + (size_t)c.a_stages * c.a_stage_bytes;
     const uint32_t bar0 = smem_u32(bars);
     auto a_full = [&](int s) { return bar0 + 8u * s; };
-    auto a_empty = [&](int s) { return bar0 + 8u * (A_STAGES + s); };
-    auto b_full = [&](int s) { return bar0 + 8u * (2 * A_STAGES + s); };
-    auto b_empty = [&](int s) { return bar0 + 8u * (2 * A_STAGES + B_STAGES + s); };
-    const uint32_t acc_full = bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES);
-    const uint32_t acc_empty = acc_full + 8u;
+    auto a_empty = [&](int s) { return bar0 + 8u * (MAX_A_STAGES + s); };
+    auto b_full = [&](int s) { return bar0 + 8u * (2 * MAX_A_STAGES + s); };
+    auto b_empty = [&](int s) { return bar0 + 8u * (2 * MAX_A_STAGES + MAX_B_STAGES + s); };
+    const uint32_t w_full = bar0 + 8u * (2 * MAX_A_STAGES + 2 * MAX_B_STAGES);
+    auto acc_full = [&](int s) { return w_full + 8u * (1 + s); };
+    auto acc_empty = [&](int s) { return w_full + 8u * (3 + s); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < A_STAGES; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < B_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 4);
+        for (int s = 0; s < MAX_A_STAGES; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < MAX_B_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        mbar_init(w_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -149,11 +190,19 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) k_conv_umma(const ConvParams 
     const int KC = p.Kt / 8;                       // K chunks per tap in the packed weights
 
     if (warp == 0) {
-        // ===== producer =====
+        // ===== producer: one thread issues every bulk copy =====
         if (lane == 0) {
             int as = 0, aph = 0, bs = 0, bph = 0;
             const unsigned char* act = reinterpret_cast<const unsigned char*>(p.a);
             const unsigned char* wts = reinterpret_cast<const unsigned char*>(p.w);
+            if (c.b_resident) {
+                mbar_expect_tx(w_full, (uint32_t)c.b_total_bytes);
+                const uint32_t bdst = smem_u32(b_smem);
+                for (int off = 0; off < c.b_total_bytes; off += 16384) {
+                    const int n = c.b_total_bytes - off < 16384 ? c.b_total_bytes - off : 16384;
+                    bulk_g2s(bdst + off, wts + off, (uint32_t)n, w_full);
+                }
+            }
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 const int im = item / c.nslices, ns = item - im * c.nslices;
                 const size_t row0 = (size_t)p.g.base0 + (size_t)im * c.J * MTILE - c.halo;
@@ -164,75 +213,122 @@ __global__ void __launch_bounds__(UMMA_THREADS, 2) k_conv_umma(const ConvParams 
                     for (int ch = 0; ch < chunks; ++ch)
                         bulk_g2s(adst + (uint32_t)ch * c.win_rows * 16,
                                  act + ((size_t)(s * chunks + ch) * p.g.Ptot + row0) * 16, (uint32_t)c.win_rows * 16, a_full(as));
-                    if (++as == A_STAGES) { as = 0; aph ^= 1; }
-                    for (int tap = 0; tap < p.ntaps; ++tap) {
-                        mbar_wait(b_empty(bs), bph ^ 1);
-                        mbar_expect_tx(b_full(bs), (uint32_t)c.b_stage_bytes);
-                        const uint32_t bdst = smem_u32(b_smem + (size_t)bs * c.b_stage_bytes);
-                        for (int ch = 0; ch < chunks; ++ch)
-                            bulk_g2s(bdst + (uint32_t)ch * c.ncta * 16,
-                                     wts + (((size_t)tap * KC + s * chunks + ch) * p.N + (size_t)ns * c.ncta) * 16,
-                                     (uint32_t)c.ncta * 16, b_full(bs));
-                        if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
+                    if (++as == c.a_stages) { as = 0; aph ^= 1; }
+                    if (!c.b_resident) {
+                        for (int tap = 0; tap < p.ntaps; ++tap) {
+                            mbar_wait(b_empty(bs), bph ^ 1);
+                            mbar_expect_tx(b_full(bs), (uint32_t)c.b_stage_bytes);
+                            const uint32_t bdst = smem_u32(b_smem + (size_t)bs * c.b_stage_bytes);
+                            for (int ch = 0; ch < chunks; ++ch)
+                                bulk_g2s(bdst + (uint32_t)ch * c.ncta * 16,
+                                         wts + (((size_t)tap * KC + s * chunks + ch) * p.N + (size_t)ns * c.ncta) * 16,
+                                         (uint32_t)c.ncta * 16, b_full(bs));
+                            if (++bs == c.b_stages) { bs = 0; bph ^= 1; }
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            int as = 0, aph = 0, bs = 0, bph = 0, accph = 0;
-            const uint32_t idesc = instr_desc_f16(MTILE, c.ncta);
-            const uint32_t a_lbo = (uint32_t)c.win_rows * 16, b_lbo = (uint32_t)c.ncta * 16;
-            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-                mbar_wait(acc_empty, accph ^ 1);
+        // ===== MMA issuer: the whole warp walks the (warp-uniform) loop nest, lane 0 issues =====
+        const uint32_t leader = lane == 0;
+        int as = 0, aph = 0, bs = 0, bph = 0, acs = 0, accph = 0;
+        const uint32_t idesc = instr_desc_f16(MTILE, c.ncta);
+        const uint32_t a_lbo = (uint32_t)c.win_rows * 16;
+        const uint32_t b_lbo = (uint32_t)(c.b_resident ? p.N : c.ncta) * 16;
+        // descriptors are advanced by adding 16-byte units to their 14-bit start-address field
+        const uint64_t a_desc0 = smem_desc(smem_u32(a_smem), a_lbo, 128);
+        const uint64_t b_desc0 = smem_desc(smem_u32(b_smem), b_lbo, 128);
+        const uint32_t a_stage_u = (uint32_t)c.a_stage_bytes >> 4, b_stage_u = (uint32_t)c.b_stage_bytes >> 4;
+        const uint32_t a_kk = (2 * a_lbo) >> 4, b_kk = (2 * b_lbo) >> 4;
+        const int KK = c.BK / 16;
+        if (c.b_resident) mbar_wait(w_full, 0);
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const int ns = item % c.nslices;
+            mbar_wait(acc_empty(acs), accph ^ 1);
+            tc_fence_after();
+            const uint32_t dcol = tmem + (uint32_t)(acs * ACC_STAGE_COLS);
+            for (int s = 0; s < nslabs; ++s) {
+                mbar_wait(a_full(as), aph);
                 tc_fence_after();
-                for (int s = 0; s < nslabs; ++s) {
-                    mbar_wait(a_full(as), aph);
-                    const uint32_t abase = smem_u32(a_smem + (size_t)as * c.a_stage_bytes);
-                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                const uint64_t ad_s = a_desc0 + (uint64_t)((uint32_t)as * a_stage_u + (uint32_t)c.halo);
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    uint64_t bd;
+                    if (c.b_resident) {
+                        bd = b_desc0 + (uint64_t)((uint32_t)((tap * KC + s * chunks) * p.N + ns * c.ncta));
+                    } else {
                         mbar_wait(b_full(bs), bph);
                         tc_fence_after();
-                        const uint32_t bbase = smem_u32(b_smem + (size_t)bs * c.b_stage_bytes);
-                        for (int j = 0; j < c.J; ++j) {
-                            const uint32_t arow = abase + (uint32_t)(j * MTILE + c.halo + p.off[tap]) * 16;
-                            for (int kk = 0; kk < c.BK / 16; ++kk) {
-                                const uint64_t ad = smem_desc(arow + (uint32_t)(2 * kk) * a_lbo, a_lbo, 128);
-                                const uint64_t bd = smem_desc(bbase + (uint32_t)(2 * kk) * b_lbo, b_lbo, 128);
-                                tc_mma_f16(tmem + (uint32_t)(j * c.ncta), ad, bd, idesc, (s | tap | kk) != 0);
-                            }
-                        }
-                        tc_commit(b_empty(bs));
-                        if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
+                        bd = b_desc0 + (uint64_t)((uint32_t)bs * b_stage_u);
                     }
-                    tc_commit(a_empty(as));
-                    if (++as == A_STAGES) { as = 0; aph ^= 1; }
+                    const uint64_t ad_t = ad_s + (uint64_t)(int64_t)p.off[tap];
+                    const uint32_t first = (s | tap) != 0;
+                    for (int j = 0; j < c.J; ++j) {
+                        const uint64_t ad_j = ad_t + (uint64_t)(j * MTILE);
+                        const uint32_t d = dcol + (uint32_t)(j * c.ncta);
+                        if (KK == 4) {
+                            tc_mma_f16_pred(d, ad_j, bd, idesc, first, leader);
+                            tc_mma_f16_pred(d, ad_j + a_kk, bd + b_kk, idesc, 1, leader);
+                            tc_mma_f16_pred(d, ad_j + 2 * a_kk, bd + 2 * b_kk, idesc, 1, leader);
+                            tc_mma_f16_pred(d, ad_j + 3 * a_kk, bd + 3 * b_kk, idesc, 1, leader);
+                        } else {
+                            for (int kk = 0; kk < KK; ++kk)
+                                tc_mma_f16_pred(d, ad_j + (uint64_t)(kk * a_kk), bd + (uint64_t)(kk * b_kk), idesc, first | (kk != 0), leader);
+                        }
+                    }
+                    if (!c.b_resident) {
+                        tc_commit_pred(b_empty(bs), leader);
+                        if (++bs == c.b_stages) { bs = 0; bph ^= 1; }
+                    }
                 }
-                tc_commit(acc_full);
-                accph ^= 1;
+                tc_commit_pred(a_empty(as), leader);
+                if (++as == c.a_stages) { as = 0; aph ^= 1; }
             }
+            tc_commit_pred(acc_full(acs), leader);
+            if (++acs == 2) { acs = 0; accph ^= 1; }
         }
     } else {
-        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 =====
-        const int q = warp & 3;
-        int accph = 0;
+        // ===== epilogue: warp e owns TMEM lanes 32*(warp%4) .. +31 and every second 32-column block =====
+        const int e = warp - 2, q = warp & 3, half = e >> 2;
+        const int nb32 = c.ncta / 32;
+        int acs = 0, accph = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
             const int im = item / c.nslices, ns = item - im * c.nslices;
-            mbar_wait(acc_full, accph);
+            mbar_wait(acc_full(acs), accph);
             tc_fence_after();
+            const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acs * ACC_STAGE_COLS);
             for (int j = 0; j < c.J; ++j) {
                 const int m = (im * c.J + j) * MTILE + q * 32 + lane;
                 const RowCtx rc = make_row_ctx(p, m);
-                for (int nb = 0; nb < c.ncta; nb += 16) {
-                    float v[16];
-                    tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * c.ncta + nb), v);
-                    if (rc.valid) epilogue_store16<__half>(p, rc, ns * c.ncta + nb, v);
+                for (int b = 0; b < nb32; ++b) {
+                    if (((j * nb32 + b) & 1) != half) continue;
+                    const int n0 = ns * c.ncta + b * 32;
+                    uint32_t r0[16], r1[16];
+                    tc_ld16_nowait(tbase + (uint32_t)(j * c.ncta + b * 32), r0);
+                    tc_ld16_nowait(tbase + (uint32_t)(j * c.ncta + b * 32 + 16), r1);
+                    float add0[16], add1[16];
+                    EpiAddr a0, a1;
+                    if (rc.valid) {
+                        a0 = epi_addr(p, rc, n0); a1 = epi_addr(p, rc, n0 + 16);
+                        epi_load16(p, a0, add0); epi_load16(p, a1, add1);
+                    }
+                    tc_ld_wait16(r0);
+                    tc_ld_wait16(r1);
+                    if (rc.valid) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
+                        epi_store16_half(p, rc, a0, n0, v, add0);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
+                        epi_store16_half(p, rc, a1, n0 + 16, v, add1);
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);
-            accph ^= 1;
+            if (lane == 0) mbar_arrive(acc_empty(acs));
+            if (++acs == 2) { acs = 0; accph ^= 1; }
         }
     }
     tc_fence_before();
@@ -285,24 +381,30 @@ int conv_umma_init() {
 
 static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     UmmaCfg c;
-    if (p.N % 16 || p.Kt % 16) { set_error("conv_umma: N=%d / K=%d must be multiples of 16", p.N, p.Kt); return GD_EUNSUPPORTED; }
+    memset(&c, 0, sizeof(c));
+    if (p.N % 32 || p.Kt % 16) { set_error("conv_umma: N=%d must be a multiple of 32 and K=%d of 16", p.N, p.Kt); return GD_EUNSUPPORTED; }
     c.ncta = p.N < 128 ? p.N : 128;
     if (p.N % c.ncta) { set_error("conv_umma: N=%d is not a multiple of %d", p.N, c.ncta); return GD_EUNSUPPORTED; }
     c.nslices = p.N / c.ncta;
-    c.BK = c.ncta >= 128 ? 32 : (p.Kt < 64 ? p.Kt : 64);
+    c.BK = p.Kt < 64 ? p.Kt : 64;
     if (p.Kt % c.BK) c.BK = 16;
     c.halo = p.ntaps == 9 ? p.g.Wp + 1 : 0;
-    c.J = TMEM_COLS / c.ncta;
+    c.b_total_bytes = p.ntaps * p.Kt * p.N * 2;
+    c.b_resident = (size_t)c.b_total_bytes <= B_RESIDENT_MAX;
+    c.b_stage_bytes = c.ncta * c.BK * 2;
+    c.b_stages = c.b_resident ? 0 : 6;
+    const size_t b_region = c.b_resident ? (size_t)c.b_total_bytes : (size_t)c.b_stages * c.b_stage_bytes;
+    c.J = ACC_STAGE_COLS / c.ncta;
     if (c.J > 4) c.J = 4;
     for (;; --c.J) {
         c.win_rows = MTILE * c.J + 2 * c.halo;
         c.a_stage_bytes = c.win_rows * c.BK * 2;
-        c.b_stage_bytes = c.ncta * c.BK * 2;
-        c.smem = (size_t)A_STAGES * c.a_stage_bytes + (size_t)B_STAGES * c.b_stage_bytes;
-        if (c.smem <= UMMA_SMEM_MAX || c.J == 1) break;
+        if (b_region + 2 * (size_t)c.a_stage_bytes <= UMMA_SMEM_MAX || c.J == 1) break;
     }
-    if (c.smem > UMMA_SMEM_MAX) { set_error("conv_umma: layer does not fit shared memory (%zu bytes)", c.smem); return GD_EUNSUPPORTED; }
-    if (c.smem < UMMA_SMEM_MIN) c.smem = UMMA_SMEM_MIN;
+    c.a_stages = (int)((UMMA_SMEM_MAX - b_region) / c.a_stage_bytes);
+    if (c.a_stages > MAX_A_STAGES) c.a_stages = MAX_A_STAGES;
+    if (c.a_stages < 2) { set_error("conv_umma: layer does not fit shared memory"); return GD_EUNSUPPORTED; }
+    c.smem = (size_t)c.a_stages * c.a_stage_bytes + b_region;
     const int tiles = (p.g.M + MTILE - 1) / MTILE;
     c.items_m = (tiles + c.J - 1) / c.J;
     *out = c;
@@ -316,7 +418,7 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t st) {
     if (rc != GD_OK) return rc;
     if (!g_num_sms) { set_error("conv_umma: library not initialised"); return GD_ECUDA; }
     const int items = c.items_m * c.nslices;
-    const int grid = items < 2 * g_num_sms ? items : 2 * g_num_sms;
+    const int grid = items < g_num_sms ? items : g_num_sms;
     cudaEvent_t e1 = nullptr;
     if (g_timing.on) {
         cudaEvent_t e0 = g_timing.get();
