@@ -115,6 +115,31 @@ __device__ __forceinline__ void tc_mma_f16_pred(uint32_t d_tmem, uint64_t adesc,
 __device__ __forceinline__ void tc_commit_pred(uint32_t bar, uint32_t) {
     if (elect_one()) tc_commit(bar);
 }
+// accumulate variant with a constant-true predicate (no register -> uniform-predicate shuffling in SASS)
+__device__ __forceinline__ void tc_mma_f16_acc(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.eq.u32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+// All J x KK MMAs of one (K-slab, tap): straight-line code issued by ONE elected lane, operands warp-uniform.
+template <int J, int KK>
+__device__ __forceinline__ void tc_mma_tap(uint32_t dcol, uint32_t ncta, uint64_t ad_t, uint64_t bd, uint32_t a_kk, uint32_t b_kk,
+                                           uint32_t idesc, uint32_t not_first) {
+    if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const uint32_t d = dcol + (uint32_t)j * ncta;
+            const uint64_t ad_j = ad_t + (uint64_t)(j * MTILE);
+            tc_mma_f16(d, ad_j, bd, idesc, not_first);
+#pragma unroll
+            for (int kk = 1; kk < KK; ++kk) tc_mma_f16_acc(d, ad_j + (uint64_t)(kk * a_kk), bd + (uint64_t)(kk * b_kk), idesc);
+        }
+    }
+    __syncwarp();
+}
 __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -152,6 +177,7 @@ __device__ __forceinline__ uint32_t instr_desc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+template <int J, int KK>
 __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams p, const UmmaCfg c) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 5];
@@ -172,7 +198,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
         for (int s = 0; s < MAX_A_STAGES; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
         for (int s = 0; s < MAX_B_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         mbar_init(w_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), EPI_WARPS); }
+        const int nu_all = J * (c.ncta / 32);
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), nu_all >= 2 ? EPI_WARPS : EPI_WARPS / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -205,7 +232,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
             }
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 const int im = item / c.nslices, ns = item - im * c.nslices;
-                const size_t row0 = (size_t)p.g.base0 + (size_t)im * c.J * MTILE - c.halo;
+                const size_t row0 = (size_t)p.g.base0 + (size_t)im * J * MTILE - c.halo;
                 for (int s = 0; s < nslabs; ++s) {
                     mbar_wait(a_empty(as), aph ^ 1);
                     mbar_expect_tx(a_full(as), (uint32_t)c.a_stage_bytes);
@@ -241,7 +268,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
         const uint64_t b_desc0 = smem_desc(smem_u32(b_smem), b_lbo, 128);
         const uint32_t a_stage_u = (uint32_t)c.a_stage_bytes >> 4, b_stage_u = (uint32_t)c.b_stage_bytes >> 4;
         const uint32_t a_kk = (2 * a_lbo) >> 4, b_kk = (2 * b_lbo) >> 4;
-        const int KK = c.BK / 16;
+        const uint32_t ncta = (uint32_t)c.ncta;
         if (c.b_resident) mbar_wait(w_full, 0);
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
             const int ns = item % c.nslices;
@@ -262,20 +289,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                         bd = b_desc0 + (uint64_t)((uint32_t)bs * b_stage_u);
                     }
                     const uint64_t ad_t = ad_s + (uint64_t)(int64_t)p.off[tap];
-                    const uint32_t first = (s | tap) != 0;
-                    for (int j = 0; j < c.J; ++j) {
-                        const uint64_t ad_j = ad_t + (uint64_t)(j * MTILE);
-                        const uint32_t d = dcol + (uint32_t)(j * c.ncta);
-                        if (KK == 4) {
-                            tc_mma_f16_pred(d, ad_j, bd, idesc, first, leader);
-                            tc_mma_f16_pred(d, ad_j + a_kk, bd + b_kk, idesc, 1, leader);
-                            tc_mma_f16_pred(d, ad_j + 2 * a_kk, bd + 2 * b_kk, idesc, 1, leader);
-                            tc_mma_f16_pred(d, ad_j + 3 * a_kk, bd + 3 * b_kk, idesc, 1, leader);
-                        } else {
-                            for (int kk = 0; kk < KK; ++kk)
-                                tc_mma_f16_pred(d, ad_j + (uint64_t)(kk * a_kk), bd + (uint64_t)(kk * b_kk), idesc, first | (kk != 0), leader);
-                        }
-                    }
+                    tc_mma_tap<J, KK>(dcol, ncta, ad_t, bd, a_kk, b_kk, idesc, (uint32_t)((s | tap) != 0));
                     if (!c.b_resident) {
                         tc_commit_pred(b_empty(bs), leader);
                         if (++bs == c.b_stages) { bs = 0; bph ^= 1; }
@@ -288,47 +302,71 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
             if (++acs == 2) { acs = 0; accph ^= 1; }
         }
     } else {
-        // ===== epilogue: warp e owns TMEM lanes 32*(warp%4) .. +31 and every second 32-column block =====
+        // ===== epilogue: warp e owns TMEM lanes 32*(warp%4) .. +31 and every second 32-column unit of an item.
+        // Software-pipelined over units (also across items): the residual/skip loads of unit u+1 are in flight while
+        // unit u waits for its accumulator, is combined and stored.
         const int e = warp - 2, q = warp & 3, half = e >> 2;
-        const int nb32 = c.ncta / 32;
-        int acs = 0, accph = 0;
-        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-            const int im = item / c.nslices, ns = item - im * c.nslices;
-            mbar_wait(acc_full(acs), accph);
-            tc_fence_after();
-            const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acs * ACC_STAGE_COLS);
-            for (int j = 0; j < c.J; ++j) {
-                const int m = (im * c.J + j) * MTILE + q * 32 + lane;
-                const RowCtx rc = make_row_ctx(p, m);
-                for (int b = 0; b < nb32; ++b) {
-                    if (((j * nb32 + b) & 1) != half) continue;
-                    const int n0 = ns * c.ncta + b * 32;
-                    uint32_t r0[16], r1[16];
-                    tc_ld16_nowait(tbase + (uint32_t)(j * c.ncta + b * 32), r0);
-                    tc_ld16_nowait(tbase + (uint32_t)(j * c.ncta + b * 32 + 16), r1);
-                    float add0[16], add1[16];
-                    EpiAddr a0, a1;
-                    if (rc.valid) {
-                        a0 = epi_addr(p, rc, n0); a1 = epi_addr(p, rc, n0 + 16);
-                        epi_load16(p, a0, add0); epi_load16(p, a1, add1);
-                    }
-                    tc_ld_wait16(r0);
-                    tc_ld_wait16(r1);
-                    if (rc.valid) {
-                        float v[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
-                        epi_store16_half(p, rc, a0, n0, v, add0);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
-                        epi_store16_half(p, rc, a1, n0 + 16, v, add1);
-                    }
+        const int nb32 = c.ncta / 32, nu = J * nb32;
+        if (half < nu) {
+            int acs = 0, accph = 0;
+            int item = blockIdx.x, u = half;
+            RowCtx rcA;
+            EpiAddr aA0, aA1;
+            float addA[32];
+            int n0A = 0;
+            auto setup = [&](int it, int uu, RowCtx& rc, EpiAddr& a0, EpiAddr& a1, int& n0, float* add) {
+                const int im = it / c.nslices, ns = it - im * c.nslices;
+                const int j = uu / nb32, b = uu - j * nb32;
+                rc = make_row_ctx(p, (im * J + j) * MTILE + q * 32 + lane);
+                n0 = ns * c.ncta + b * 32;
+                if (rc.valid) {
+                    a0 = epi_addr(p, rc, n0); a1 = epi_addr(p, rc, n0 + 16);
+                    epi_load16(p, a0, add); epi_load16(p, a1, add + 16);
                 }
+            };
+            bool have = item < total_items;
+            if (have) setup(item, u, rcA, aA0, aA1, n0A, addA);
+            while (have) {
+                if (u == half) {
+                    mbar_wait(acc_full(acs), accph);
+                    tc_fence_after();
+                }
+                const int j = u / nb32, b = u - j * nb32;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acs * ACC_STAGE_COLS + j * c.ncta + b * 32);
+                uint32_t r0[16], r1[16];
+                tc_ld16_nowait(taddr, r0);
+                tc_ld16_nowait(taddr + 16, r1);
+                int nitem = item, nuu = u + 2;
+                if (nuu >= nu) { nitem += gridDim.x; nuu = half; }
+                const bool haveN = nitem < total_items;
+                RowCtx rcB;
+                EpiAddr aB0, aB1;
+                float addB[32];
+                int n0B = 0;
+                rcB.valid = false;
+                if (haveN) setup(nitem, nuu, rcB, aB0, aB1, n0B, addB);
+                tc_ld_wait16(r0);
+                tc_ld_wait16(r1);
+                if (rcA.valid) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
+                    epi_store16_half(p, rcA, aA0, n0A, v, addA);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
+                    epi_store16_half(p, rcA, aA1, n0A + 16, v, addA + 16);
+                }
+                if (nitem != item) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty(acs));
+                    if (++acs == 2) { acs = 0; accph ^= 1; }
+                }
+                item = nitem; u = nuu; have = haveN;
+                rcA = rcB; aA0 = aB0; aA1 = aB1; n0A = n0B;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) addA[i] = addB[i];
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty(acs));
-            if (++acs == 2) { acs = 0; accph ^= 1; }
         }
     }
     tc_fence_before();
@@ -375,7 +413,9 @@ int conv_umma_init() {
     int dev;
     GD_CUDA_CHECK(cudaGetDevice(&dev));
     GD_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    GD_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX));
+#define GD_UMMA_ATTR(J, KK) GD_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma<J, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX))
+    GD_UMMA_ATTR(1, 2); GD_UMMA_ATTR(2, 2); GD_UMMA_ATTR(4, 2); GD_UMMA_ATTR(1, 4); GD_UMMA_ATTR(2, 4); GD_UMMA_ATTR(4, 4);
+#undef GD_UMMA_ATTR
     return GD_OK;
 }
 
@@ -386,8 +426,8 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     c.ncta = p.N < 128 ? p.N : 128;
     if (p.N % c.ncta) { set_error("conv_umma: N=%d is not a multiple of %d", p.N, c.ncta); return GD_EUNSUPPORTED; }
     c.nslices = p.N / c.ncta;
-    c.BK = p.Kt < 64 ? p.Kt : 64;
-    if (p.Kt % c.BK) c.BK = 16;
+    c.BK = p.Kt % 64 == 0 ? 64 : 32;
+    if (p.Kt % c.BK) { set_error("conv_umma: K=%d must be a multiple of 32", p.Kt); return GD_EUNSUPPORTED; }
     c.halo = p.ntaps == 9 ? p.g.Wp + 1 : 0;
     c.b_total_bytes = p.ntaps * p.Kt * p.N * 2;
     c.b_resident = (size_t)c.b_total_bytes <= B_RESIDENT_MAX;
@@ -396,7 +436,7 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     const size_t b_region = c.b_resident ? (size_t)c.b_total_bytes : (size_t)c.b_stages * c.b_stage_bytes;
     c.J = ACC_STAGE_COLS / c.ncta;
     if (c.J > 4) c.J = 4;
-    for (;; --c.J) {
+    for (;; c.J >>= 1) {
         c.win_rows = MTILE * c.J + 2 * c.halo;
         c.a_stage_bytes = c.win_rows * c.BK * 2;
         if (b_region + 2 * (size_t)c.a_stage_bytes <= UMMA_SMEM_MAX || c.J == 1) break;
@@ -427,7 +467,11 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t st) {
         g_timing.flops.push_back(2.0 * (double)(p.g.M / p.g.S) * p.g.H * p.g.W * (double)p.N * p.Kt * p.ntaps);
         GD_CUDA_CHECK(cudaEventRecord(e0, st));
     }
-    k_conv_umma<<<grid, UMMA_THREADS, c.smem, st>>>(p, c);
+    const int KK = c.BK / 16;
+#define GD_UMMA_GO(JJ, KKK) if (c.J == JJ && KK == KKK) k_conv_umma<JJ, KKK><<<grid, UMMA_THREADS, c.smem, st>>>(p, c); else
+    GD_UMMA_GO(1, 2) GD_UMMA_GO(2, 2) GD_UMMA_GO(4, 2) GD_UMMA_GO(1, 4) GD_UMMA_GO(2, 4) GD_UMMA_GO(4, 4)
+    { set_error("conv_umma: no kernel variant for J=%d, BK=%d", c.J, c.BK); return GD_EUNSUPPORTED; }
+#undef GD_UMMA_GO
     GD_LAUNCHED();
     if (e1) GD_CUDA_CHECK(cudaEventRecord(e1, st));
     return GD_OK;
