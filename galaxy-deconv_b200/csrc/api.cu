@@ -466,7 +466,7 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
     auto up_stage = [&](int L, int s0, int n) -> int {            // m_up{L+1} (ResUNet.py:36-38)
         ConvParams p = conv_base(g[L + 1], n);         // k2s2 transposed conv: GEMM on the coarse level, scatter to fine
         p.ntaps = 1; p.off[0] = 0; p.Kt = C[L + 1]; p.N = 4 * C[L]; p.a = at(ws.a16[L + 1], L + 1, s0); p.w = W->up[L];
-        p.mode = 1; p.Cf = C[L]; p.gf = g[L]; p.gf.M = n * g[L].S;
+        p.mode = 1; p.Cf = C[L]; p.Cf_log2 = 0; while ((1 << p.Cf_log2) < p.Cf) ++p.Cf_log2; p.gf = g[L]; p.gf.M = n * g[L].S;
         p.out32 = (float*)at(ws.p32a[L], L, s0); p.out16 = at(ws.a16[L], L, s0);
         GD_TRY(run_conv(p, prec, st));
         GD_TRY(resblock(L, s0, n, W->up_rb[L][0], ws.p32a[L], nullptr, ws.p32b[L], ws.a16[L], nullptr));

@@ -23,8 +23,8 @@ __device__ __forceinline__ RowCtx make_row_ctx(const ConvParams& p, int m) {
     const Geom& g = p.g;
     c.valid = false; c.row = g.base0 + m; c.crow = 0; c.ctap = 0; c.frow0 = 0;
     if (m >= g.M) return c;
-    int b = m / g.S, r = m - b * g.S;
-    int y = r / g.Wp, x = r - y * g.Wp;
+    int b = (int)div_by_magic((uint32_t)m, g.magS, g.shS), r = m - b * g.S;
+    int y = (int)div_by_magic((uint32_t)r, g.magW, g.shW), x = r - y * g.Wp;
     if (y >= g.H || x >= g.W) return c;
     c.valid = true;
     if (p.s2d) {
@@ -103,8 +103,8 @@ struct EpiAddr { int row, Ptot, c0; };
 __device__ __forceinline__ EpiAddr epi_addr(const ConvParams& p, const RowCtx& rc, int n0) {
     EpiAddr a;
     if (p.mode == 1) {
-        int tap = n0 / p.Cf;
-        a.c0 = n0 - tap * p.Cf;
+        int tap = n0 >> p.Cf_log2;              // Cf is a power of two (32 .. 256)
+        a.c0 = n0 & (p.Cf - 1);
         a.row = rc.frow0 + (tap >> 1) * p.gf.Wp + (tap & 1);
         a.Ptot = p.gf.Ptot;
     } else {
@@ -133,6 +133,15 @@ __device__ __forceinline__ void epi_load16(const ConvParams& p, const EpiAddr& a
     }
 }
 
+// one 16-column group of an fp32 stream tensor
+__device__ __forceinline__ void epi_load16_one(const float* src, const EpiAddr& a, float* r) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(src + ((size_t)(a.c0 / 4 + q) * a.Ptot + a.row) * 4));
+        r[4 * q] = t.x; r[4 * q + 1] = t.y; r[4 * q + 2] = t.z; r[4 * q + 3] = t.w;
+    }
+}
+
 __device__ __forceinline__ uint4 pack8_half(const float* v) {
     __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
     __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
@@ -154,6 +163,28 @@ __device__ __forceinline__ void epi_store16_half(const ConvParams& p, const RowC
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += r[i];
     }
+    if (p.out32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(p.out32 + ((size_t)(a.c0 / 4 + q) * a.Ptot + a.row) * 4) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    if (p.out16) {
+        __half* base = reinterpret_cast<__half*>(p.out16);
+        *reinterpret_cast<uint4*>(base + ((size_t)(a.c0 / 8) * a.Ptot + a.row) * 8) = pack8_half(v);
+        *reinterpret_cast<uint4*>(base + ((size_t)(a.c0 / 8 + 1) * a.Ptot + a.row) * 8) = pack8_half(v + 8);
+    }
+    if (p.s2d) {
+        __half* base = reinterpret_cast<__half*>(p.s2d);
+        const int cb = rc.ctap * p.N + n0;
+        *reinterpret_cast<uint4*>(base + ((size_t)(cb / 8) * p.gc.Ptot + rc.crow) * 8) = pack8_half(v);
+        *reinterpret_cast<uint4*>(base + ((size_t)(cb / 8 + 1) * p.gc.Ptot + rc.crow) * 8) = pack8_half(v + 8);
+    }
+}
+
+
+// stores only (all arithmetic already applied): out32 / out16 / s2d of one 16-column group
+__device__ __forceinline__ void epi_out16(const ConvParams& p, const RowCtx& rc, const EpiAddr& a, int n0, const float* v) {
     if (p.out32) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)

@@ -22,13 +22,17 @@
 #include "kernels.cuh"
 #include "launch.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 namespace gd {
 
+enum { EPI_PLAIN = 0, EPI_FULL = 1 };
 constexpr int EPI_WARPS = 8;
-constexpr int UMMA_THREADS = 64 + 32 * EPI_WARPS;   // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int MMA_WARPS = 4;                        // warps 1..4: MMA issuers, one 128-row tile of the item each (J <= 4)
+constexpr int EPI_WARP0 = 1 + MMA_WARPS;            // warps 5..12: epilogue
+constexpr int UMMA_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_B_STAGES = 8;
 constexpr int TMEM_COLS = 512;                      // one CTA per SM owns all of TMEM: 2 accumulator stages x 256 columns
@@ -47,6 +51,8 @@ struct UmmaCfg {
     int b_resident;  // 1: all taps/K of the weights loaded once per CTA; 0: streamed per (slab, tap) through a ring
     int b_stage_bytes, b_stages, b_total_bytes;
     int items_m;     // ceil(tiles / J)
+    int nsl_log2, nb32_log2;   // log2(nslices), log2(ncta / 32): both are powers of two
+    int l2pf;        // producer prefetches the residual / skip rows of each item into L2
     size_t smem;
 };
 
@@ -82,6 +88,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// TMA-engine prefetch of a contiguous global range into L2 (no destination, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -177,7 +187,7 @@ __device__ __forceinline__ uint32_t instr_desc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int J, int KK>
+template <int J, int KK, int EPI>
 __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams p, const UmmaCfg c) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 5];
@@ -195,11 +205,11 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
     auto acc_empty = [&](int s) { return w_full + 8u * (3 + s); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < MAX_A_STAGES; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < MAX_B_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < MAX_A_STAGES; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), J); }
+        for (int s = 0; s < MAX_B_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), J); }
         mbar_init(w_full, 1);
         const int nu_all = J * (c.ncta / 32);
-        for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), nu_all >= 2 ? EPI_WARPS : EPI_WARPS / 2); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), J); mbar_init(acc_empty(s), nu_all >= 2 ? EPI_WARPS : EPI_WARPS / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -231,8 +241,16 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                 }
             }
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-                const int im = item / c.nslices, ns = item - im * c.nslices;
+                const int im = item >> c.nsl_log2, ns = item & (c.nslices - 1);
                 const size_t row0 = (size_t)p.g.base0 + (size_t)im * J * MTILE - c.halo;
+                if (c.l2pf && p.mode == 0 && (p.res32 || p.skip32)) {
+                    // the epilogue of this item will read its residual / skip rows: pull them from HBM into L2 now
+                    const size_t r0 = (size_t)p.g.base0 + (size_t)im * J * MTILE;
+                    for (int pl = ns * (c.ncta / 4); pl < (ns + 1) * (c.ncta / 4); ++pl) {
+                        if (p.res32) bulk_prefetch_l2(p.res32 + ((size_t)pl * p.g.Ptot + r0) * 4, (uint32_t)(J * MTILE * 16));
+                        if (p.skip32) bulk_prefetch_l2(p.skip32 + ((size_t)pl * p.g.Ptot + r0) * 4, (uint32_t)(J * MTILE * 16));
+                    }
+                }
                 for (int s = 0; s < nslabs; ++s) {
                     mbar_wait(a_empty(as), aph ^ 1);
                     mbar_expect_tx(a_full(as), (uint32_t)c.a_stage_bytes);
@@ -256,8 +274,13 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp walks the (warp-uniform) loop nest, lane 0 issues =====
+    } else if (warp <= MMA_WARPS) {
+      // ===== MMA issuers: warp 1+jw owns tile jw of every item (its own accumulator columns), so up to four warps on
+      // four schedulers feed the tensor pipe in parallel -- a single warp's scalar issue loop (~20 instructions per MMA)
+      // is slower than the 16..64-cycle MMAs of the narrow layers.  Each warp walks the (warp-uniform) loop nest as a
+      // whole, one elected lane issues; stage/accumulator barriers expect one commit per MMA warp. =====
+      const int jw = warp - 1;
+      if (jw < J) {
         const uint32_t leader = lane == 0;
         int as = 0, aph = 0, bs = 0, bph = 0, acs = 0, accph = 0;
         const uint32_t idesc = instr_desc_f16(MTILE, c.ncta);
@@ -271,7 +294,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
         const uint32_t ncta = (uint32_t)c.ncta;
         if (c.b_resident) mbar_wait(w_full, 0);
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-            const int ns = item % c.nslices;
+            const int ns = item & (c.nslices - 1);
             mbar_wait(acc_empty(acs), accph ^ 1);
             tc_fence_after();
             const uint32_t dcol = tmem + (uint32_t)(acs * ACC_STAGE_COLS);
@@ -289,7 +312,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                         bd = b_desc0 + (uint64_t)((uint32_t)bs * b_stage_u);
                     }
                     const uint64_t ad_t = ad_s + (uint64_t)(int64_t)p.off[tap];
-                    tc_mma_tap<J, KK>(dcol, ncta, ad_t, bd, a_kk, b_kk, idesc, (uint32_t)((s | tap) != 0));
+                    tc_mma_tap<1, KK>(dcol + (uint32_t)jw * ncta, ncta, ad_t + (uint64_t)(jw * MTILE), bd, a_kk, b_kk, idesc, (uint32_t)((s | tap) != 0));
                     if (!c.b_resident) {
                         tc_commit_pred(b_empty(bs), leader);
                         if (++bs == c.b_stages) { bs = 0; bph ^= 1; }
@@ -301,71 +324,120 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
             tc_commit_pred(acc_full(acs), leader);
             if (++acs == 2) { acs = 0; accph ^= 1; }
         }
+      }
     } else {
         // ===== epilogue: warp e owns TMEM lanes 32*(warp%4) .. +31 and every second 32-column unit of an item.
-        // Software-pipelined over units (also across items): the residual/skip loads of unit u+1 are in flight while
-        // unit u waits for its accumulator, is combined and stored.
-        const int e = warp - 2, q = warp & 3, half = e >> 2;
+        // Lean, specialised per layer kind (EPI): EPI_PLAIN = ReLU? + fp16 copy only (first conv of a ResBlock);
+        // EPI_FULL = residual / skip / fp32 stream / fp16 copy / space-to-depth / pixel-shuffle.  The fp32 residual of
+        // unit u of the NEXT item is requested as soon as the registers of unit u of this item have been consumed, so
+        // its HBM latency hides behind the rest of this item and the wait for the next accumulator.
+        const int e = warp - EPI_WARP0, q = warp & 3, half = e >> 2;
         const int nb32 = c.ncta / 32, nu = J * nb32;
+        constexpr int UPW_MAX = 4;                       // units per warp and item: nu / 2 <= 4 (J * ncta <= 256)
+        const int upw = nu >> 1;
         if (half < nu) {
             int acs = 0, accph = 0;
-            int item = blockIdx.x, u = half;
-            RowCtx rcA;
-            EpiAddr aA0, aA1;
-            float addA[32];
-            int n0A = 0;
-            auto setup = [&](int it, int uu, RowCtx& rc, EpiAddr& a0, EpiAddr& a1, int& n0, float* add) {
-                const int im = it / c.nslices, ns = it - im * c.nslices;
-                const int j = uu / nb32, b = uu - j * nb32;
-                rc = make_row_ctx(p, (im * J + j) * MTILE + q * 32 + lane);
-                n0 = ns * c.ncta + b * 32;
-                if (rc.valid) {
-                    a0 = epi_addr(p, rc, n0); a1 = epi_addr(p, rc, n0 + 16);
-                    epi_load16(p, a0, add); epi_load16(p, a1, add + 16);
+            const Geom& g = p.g;
+            const uint32_t Ptot = (uint32_t)g.Ptot;
+            constexpr int UPW_PREF = 2;                      // units per warp whose residual is prefetched one item ahead
+            float add[EPI == EPI_FULL ? UPW_PREF : 1][32];
+            // row decomposition of GEMM row m: validity + absolute row (+ s2d / pixel-shuffle targets via make_row_ctx)
+            auto unit_of = [&](int i) { return nu == 1 ? 0 : half + 2 * i; };
+            auto issue_res = [&](int item, int i) {
+                if (EPI != EPI_FULL || !p.res32 || p.mode == 1 || i >= UPW_PREF) return;
+                const int im = item >> c.nsl_log2, ns = item & (c.nslices - 1);
+                const int uu = unit_of(i), j = uu >> c.nb32_log2, b = uu & (nb32 - 1);
+                const int m = (im * J + j) * MTILE + q * 32 + lane;
+                if (m >= g.M) return;
+                const float4* src = reinterpret_cast<const float4*>(p.res32) + (size_t)((ns * c.ncta + b * 32) >> 2) * Ptot + (g.base0 + m);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float4 t = __ldg(src + (size_t)k * Ptot);
+                    float* d = add[EPI == EPI_FULL && i < UPW_PREF ? i : 0];
+                    d[4 * k] = t.x; d[4 * k + 1] = t.y; d[4 * k + 2] = t.z; d[4 * k + 3] = t.w;
                 }
             };
-            bool have = item < total_items;
-            if (have) setup(item, u, rcA, aA0, aA1, n0A, addA);
-            while (have) {
-                if (u == half) {
-                    mbar_wait(acc_full(acs), accph);
-                    tc_fence_after();
-                }
-                const int j = u / nb32, b = u - j * nb32;
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acs * ACC_STAGE_COLS + j * c.ncta + b * 32);
-                uint32_t r0[16], r1[16];
-                tc_ld16_nowait(taddr, r0);
-                tc_ld16_nowait(taddr + 16, r1);
-                int nitem = item, nuu = u + 2;
-                if (nuu >= nu) { nitem += gridDim.x; nuu = half; }
-                const bool haveN = nitem < total_items;
-                RowCtx rcB;
-                EpiAddr aB0, aB1;
-                float addB[32];
-                int n0B = 0;
-                rcB.valid = false;
-                if (haveN) setup(nitem, nuu, rcB, aB0, aB1, n0B, addB);
-                tc_ld_wait16(r0);
-                tc_ld_wait16(r1);
-                if (rcA.valid) {
-                    float v[16];
+            int item = blockIdx.x;
+            if (item < total_items) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
-                    epi_store16_half(p, rcA, aA0, n0A, v, addA);
+                for (int i = 0; i < UPW_MAX; ++i)
+                    if (i < upw || (nu == 1 && i == 0)) issue_res(item, i);
+            }
+            for (; item < total_items; item += gridDim.x) {
+                const int im = item >> c.nsl_log2, ns = item & (c.nslices - 1);
+                const int nitem = item + gridDim.x;
+                mbar_wait(acc_full(acs), accph);
+                tc_fence_after();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
-                    epi_store16_half(p, rcA, aA1, n0A + 16, v, addA + 16);
-                }
-                if (nitem != item) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty(acs));
-                    if (++acs == 2) { acs = 0; accph ^= 1; }
-                }
-                item = nitem; u = nuu; have = haveN;
-                rcA = rcB; aA0 = aB0; aA1 = aB1; n0A = n0B;
+                for (int i = 0; i < UPW_MAX; ++i) {
+                    if (!(i < upw || (nu == 1 && i == 0))) continue;
+                    const int uu = unit_of(i), j = uu >> c.nb32_log2, b = uu & (nb32 - 1);
+                    const int n0 = ns * c.ncta + b * 32;
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acs * ACC_STAGE_COLS + j * c.ncta + b * 32);
+                    uint32_t r0[16], r1[16];
+                    tc_ld16_nowait(taddr, r0);
+                    tc_ld16_nowait(taddr + 16, r1);
+                    const int m = (im * J + j) * MTILE + q * 32 + lane;
+                    float v[32];
+                    if (EPI == EPI_PLAIN) {
+                        // validity only (no s2d / scatter targets needed)
+                        const uint32_t bq = div_by_magic((uint32_t)m, g.magS, g.shS), r = (uint32_t)m - bq * (uint32_t)g.S;
+                        const uint32_t y = div_by_magic(r, g.magW, g.shW), x = r - y * (uint32_t)g.Wp;
+                        const bool valid = m < g.M && (int)y < g.H && (int)x < g.W;
+                        tc_ld_wait16(r0);
+                        tc_ld_wait16(r1);
+                        if (valid) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) addA[i] = addB[i];
+                            for (int k = 0; k < 16; ++k) { v[k] = __uint_as_float(r0[k]); v[16 + k] = __uint_as_float(r1[k]); }
+                            if (p.relu) {
+#pragma unroll
+                                for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
+                            }
+                            uint4* dst = reinterpret_cast<uint4*>(p.out16) + (size_t)(n0 >> 3) * Ptot + (g.base0 + m);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) dst[(size_t)k * Ptot] = pack8_half(v + 8 * k);
+                        }
+                    } else {
+                        const RowCtx rc = make_row_ctx(p, m);
+                        tc_ld_wait16(r0);
+                        tc_ld_wait16(r1);
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) { v[k] = __uint_as_float(r0[k]); v[16 + k] = __uint_as_float(r1[k]); }
+                        if (p.relu) {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
+                        }
+                        if (p.res32 && p.mode == 0 && m < g.M) {
+                            if (i < UPW_PREF) {
+#pragma unroll
+                                for (int k = 0; k < 32; ++k) v[k] += add[EPI == EPI_FULL && i < UPW_PREF ? i : 0][k];
+                            } else {                        // units beyond the prefetch depth (streamed-weight layers): load at use
+                                const float4* src = reinterpret_cast<const float4*>(p.res32) + (size_t)(n0 >> 2) * Ptot + (g.base0 + m);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    float4 t = __ldg(src + (size_t)k * Ptot);
+                                    v[4 * k] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
+                                }
+                            }
+                        }
+                        if (nitem < total_items) issue_res(nitem, i);          // registers of unit i are free again
+                        if (rc.valid) {
+                            const EpiAddr a0 = epi_addr(p, rc, n0), a1 = epi_addr(p, rc, n0 + 16);
+                            if (p.skip32) {
+                                float sk[32];
+                                epi_load16_one(p.skip32, a0, sk); epi_load16_one(p.skip32, a1, sk + 16);
+#pragma unroll
+                                for (int k = 0; k < 32; ++k) v[k] += sk[k];
+                            }
+                            epi_out16(p, rc, a0, n0, v);
+                            epi_out16(p, rc, a1, n0 + 16, v + 16);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(acs));
+                if (++acs == 2) { acs = 0; accph ^= 1; }
             }
         }
     }
@@ -378,6 +450,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
 }
 
 static int g_num_sms = 0;
+static int g_l2pf = 0;
 
 // Optional per-launch timing of k_conv_umma with CUDA events on the launching stream (gd_profile_begin/end):
 // bench.py uses it to measure the dominant kernel's average duration live for the roofline line.
@@ -413,7 +486,10 @@ int conv_umma_init() {
     int dev;
     GD_CUDA_CHECK(cudaGetDevice(&dev));
     GD_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-#define GD_UMMA_ATTR(J, KK) GD_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma<J, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX))
+    if (const char* e = getenv("GDECONV_L2PF")) g_l2pf = atoi(e);
+#define GD_UMMA_ATTR(J, KK)                                                                                                        \
+    GD_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma<J, KK, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX)); \
+    GD_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma<J, KK, EPI_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX))
     GD_UMMA_ATTR(1, 2); GD_UMMA_ATTR(2, 2); GD_UMMA_ATTR(4, 2); GD_UMMA_ATTR(1, 4); GD_UMMA_ATTR(2, 4); GD_UMMA_ATTR(4, 4);
 #undef GD_UMMA_ATTR
     return GD_OK;
@@ -426,7 +502,7 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     c.ncta = p.N < 128 ? p.N : 128;
     if (p.N % c.ncta) { set_error("conv_umma: N=%d is not a multiple of %d", p.N, c.ncta); return GD_EUNSUPPORTED; }
     c.nslices = p.N / c.ncta;
-    c.BK = p.Kt % 64 == 0 ? 64 : 32;
+    c.BK = (p.Kt % 64 == 0 && (size_t)p.ntaps * p.Kt * p.N * 2 > B_RESIDENT_MAX) ? 64 : 32;   // streamed weights: 64-channel slabs
     if (p.Kt % c.BK) { set_error("conv_umma: K=%d must be a multiple of 32", p.Kt); return GD_EUNSUPPORTED; }
     c.halo = p.ntaps == 9 ? p.g.Wp + 1 : 0;
     c.b_total_bytes = p.ntaps * p.Kt * p.N * 2;
@@ -434,8 +510,9 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     c.b_stage_bytes = c.ncta * c.BK * 2;
     c.b_stages = c.b_resident ? 0 : 6;
     const size_t b_region = c.b_resident ? (size_t)c.b_total_bytes : (size_t)c.b_stages * c.b_stage_bytes;
-    c.J = ACC_STAGE_COLS / c.ncta;
-    if (c.J > 4) c.J = 4;
+    // resident weights: <= 128 accumulator columns per item (2 epilogue units per warp, fine-grained A ring, good tail
+    // balance); streamed weights: 256 columns so that every weight stage is reused by twice as many rows
+    c.J = (c.b_resident ? 128 : ACC_STAGE_COLS) / c.ncta;
     for (;; c.J >>= 1) {
         c.win_rows = MTILE * c.J + 2 * c.halo;
         c.a_stage_bytes = c.win_rows * c.BK * 2;
@@ -447,6 +524,10 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     c.smem = (size_t)c.a_stages * c.a_stage_bytes + b_region;
     const int tiles = (p.g.M + MTILE - 1) / MTILE;
     c.items_m = (tiles + c.J - 1) / c.J;
+    c.l2pf = g_l2pf;
+    auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+    c.nsl_log2 = ilog2(c.nslices); c.nb32_log2 = ilog2(c.ncta / 32);
+    if ((1 << c.nsl_log2) != c.nslices || (1 << c.nb32_log2) != c.ncta / 32) { set_error("conv_umma: N=%d must split into power-of-two slices", p.N); return GD_EUNSUPPORTED; }
     *out = c;
     return GD_OK;
 }
@@ -468,7 +549,12 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t st) {
         GD_CUDA_CHECK(cudaEventRecord(e0, st));
     }
     const int KK = c.BK / 16;
-#define GD_UMMA_GO(JJ, KKK) if (c.J == JJ && KK == KKK) k_conv_umma<JJ, KKK><<<grid, UMMA_THREADS, c.smem, st>>>(p, c); else
+    const bool plain = p.mode == 0 && !p.res32 && !p.skip32 && !p.out32 && !p.s2d && p.out16;
+#define GD_UMMA_GO(JJ, KKK)                                                                         \
+    if (c.J == JJ && KK == KKK) {                                                                   \
+        if (plain) k_conv_umma<JJ, KKK, EPI_PLAIN><<<grid, UMMA_THREADS, c.smem, st>>>(p, c);       \
+        else k_conv_umma<JJ, KKK, EPI_FULL><<<grid, UMMA_THREADS, c.smem, st>>>(p, c);              \
+    } else
     GD_UMMA_GO(1, 2) GD_UMMA_GO(2, 2) GD_UMMA_GO(4, 2) GD_UMMA_GO(1, 4) GD_UMMA_GO(2, 4) GD_UMMA_GO(4, 4)
     { set_error("conv_umma: no kernel variant for J=%d, BK=%d", c.J, c.BK); return GD_EUNSUPPORTED; }
 #undef GD_UMMA_GO

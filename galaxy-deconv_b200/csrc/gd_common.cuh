@@ -39,11 +39,24 @@ enum Precision { PREC_FP32_SIMT = GD_PREC_FP32_SIMT, PREC_FP16_UMMA = GD_PREC_FP
 // ---------------------------------------------------------------------------------------------------
 struct Geom {
     int H, W, Wp, S, base0, Ptot, M;          // M = B*S GEMM rows to compute
+    uint32_t magS, shS, magW, shW;            // floor(n / S) = (n * magS) >> shS, floor(n / Wp) = (n * magW) >> shW
 };
+
+// Exact unsigned division of n < 2^26 by an invariant d through one 32x32->64 multiply (Granlund-Montgomery):
+// with l = ceil(log2 d), shift = 26 + l and magic = ceil(2^shift / d) < 2^27, n * (magic*d - 2^shift) < 2^shift holds
+// for every n < 2^26.  GEMM rows of a chunk stay far below 2^26 (make_geom checks).
+inline void div_magic(uint32_t d, uint32_t* magic, uint32_t* shift) {
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;
+    *shift = 26 + l;
+    *magic = (uint32_t)(((1ull << *shift) + d - 1) / d);
+}
+GD_HD uint32_t div_by_magic(uint32_t n, uint32_t magic, uint32_t shift) { return (uint32_t)(((unsigned long long)n * magic) >> shift); }
 
 inline Geom make_geom(int H, int batch) {
     Geom g;
     g.H = H; g.W = H; g.Wp = H + 1; g.S = (H + 1) * (H + 1); g.base0 = g.Wp + 1;
+    div_magic((uint32_t)g.S, &g.magS, &g.shS); div_magic((uint32_t)g.Wp, &g.magW, &g.shW);
     g.M = batch * g.S;
     int mt = ((g.M + MTILE - 1) / MTILE + 7) / 8 * 8;
     // a CTA of the tcgen05 kernel owns up to 8 consecutive tiles and its window reaches Wp+1 rows past them
@@ -76,7 +89,7 @@ struct ConvParams {
     void* s2d;                // space-to-depth copy for the following k2s2 strided conv, coarse geometry gc
     // mode 1 (transposed conv): column n = tap*Cf + c scatters to fine pixel (2Y+dy, 2X+dx), geometry gf
     int mode;
-    int Cf;
+    int Cf, Cf_log2;
     Geom gc;                  // coarse level (s2d target)
     Geom gf;                  // fine level (mode 1 target)
 };
