@@ -241,7 +241,7 @@ def main():
     F = flops_per_stamp_g(args.n_iters)
     line = dict(metric=metric, value=gal_s, unit='galaxies/s', n_gpus=world, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_step,
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f16' if precision.startswith('fp16') else 'f32',
-                data='synthetic', config=dict(cfg, precision=precision, chunk=engine.max_chunk()),
+                data='synthetic', config=dict(cfg, precision=precision, chunk=engine._chunk_for(hi - lo)),
                 e2e=dict(value=n_total / (ms_e2e * 1e-3), unit='galaxies/s', h2d_bytes_per_step=(hi - lo) * STAMP_BYTES_IN,
                          d2h_bytes_per_step=(hi - lo) * 48 * 48 * 4 + n_total * 8, ms_per_step=ms_e2e),
                 gpu_launches=launches, clocks=clocks,

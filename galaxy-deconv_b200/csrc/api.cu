@@ -424,7 +424,7 @@ static int g_subchunk = 0;
 static int subchunk_size() {
     if (!g_subchunk) {
         const char* e = getenv("GDECONV_SUBCHUNK");
-        g_subchunk = e && atoi(e) > 0 ? atoi(e) : 64;
+        g_subchunk = e && atoi(e) > 0 ? atoi(e) : (1 << 30);     // default: no sub-chunking (measured slower, profiles/)
     }
     return g_subchunk;
 }

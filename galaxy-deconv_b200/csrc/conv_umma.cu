@@ -52,6 +52,7 @@ struct UmmaCfg {
     int b_stage_bytes, b_stages, b_total_bytes;
     int items_m;     // ceil(tiles / J)
     int nsl_log2, nb32_log2;   // log2(nslices), log2(ncta / 32): both are powers of two
+    int abl;         // diagnostic ablation bits (GDECONV_ABL): 1 = no weight streaming, 2 = no epilogue global traffic, 4 = no activation loads
     int l2pf;        // producer prefetches the residual / skip rows of each item into L2
     size_t smem;
 };
@@ -253,21 +254,29 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                 }
                 for (int s = 0; s < nslabs; ++s) {
                     mbar_wait(a_empty(as), aph ^ 1);
-                    mbar_expect_tx(a_full(as), (uint32_t)c.a_stage_bytes);
-                    const uint32_t adst = smem_u32(a_smem + (size_t)as * c.a_stage_bytes);
-                    for (int ch = 0; ch < chunks; ++ch)
-                        bulk_g2s(adst + (uint32_t)ch * c.win_rows * 16,
-                                 act + ((size_t)(s * chunks + ch) * p.g.Ptot + row0) * 16, (uint32_t)c.win_rows * 16, a_full(as));
+                    if ((c.abl & 4) && aph) {
+                        mbar_arrive(a_full(as));                      // ablation: reuse whatever the stage holds
+                    } else {
+                        mbar_expect_tx(a_full(as), (uint32_t)c.a_stage_bytes);
+                        const uint32_t adst = smem_u32(a_smem + (size_t)as * c.a_stage_bytes);
+                        for (int ch = 0; ch < chunks; ++ch)
+                            bulk_g2s(adst + (uint32_t)ch * c.win_rows * 16,
+                                     act + ((size_t)(s * chunks + ch) * p.g.Ptot + row0) * 16, (uint32_t)c.win_rows * 16, a_full(as));
+                    }
                     if (++as == c.a_stages) { as = 0; aph ^= 1; }
                     if (!c.b_resident) {
                         for (int tap = 0; tap < p.ntaps; ++tap) {
                             mbar_wait(b_empty(bs), bph ^ 1);
-                            mbar_expect_tx(b_full(bs), (uint32_t)c.b_stage_bytes);
-                            const uint32_t bdst = smem_u32(b_smem + (size_t)bs * c.b_stage_bytes);
-                            for (int ch = 0; ch < chunks; ++ch)
-                                bulk_g2s(bdst + (uint32_t)ch * c.ncta * 16,
-                                         wts + (((size_t)tap * KC + s * chunks + ch) * p.N + (size_t)ns * c.ncta) * 16,
-                                         (uint32_t)c.ncta * 16, b_full(bs));
+                            if ((c.abl & 1) && bph) {
+                                mbar_arrive(b_full(bs));              // ablation: reuse whatever the stage holds
+                            } else {
+                                mbar_expect_tx(b_full(bs), (uint32_t)c.b_stage_bytes);
+                                const uint32_t bdst = smem_u32(b_smem + (size_t)bs * c.b_stage_bytes);
+                                for (int ch = 0; ch < chunks; ++ch)
+                                    bulk_g2s(bdst + (uint32_t)ch * c.ncta * 16,
+                                             wts + (((size_t)tap * KC + s * chunks + ch) * p.N + (size_t)ns * c.ncta) * 16,
+                                             (uint32_t)c.ncta * 16, b_full(bs));
+                            }
                             if (++bs == c.b_stages) { bs = 0; bph ^= 1; }
                         }
                     }
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
             // row decomposition of GEMM row m: validity + absolute row (+ s2d / pixel-shuffle targets via make_row_ctx)
             auto unit_of = [&](int i) { return nu == 1 ? 0 : half + 2 * i; };
             auto issue_res = [&](int item, int i) {
-                if (EPI != EPI_FULL || !p.res32 || p.mode == 1 || i >= UPW_PREF) return;
+                if (EPI != EPI_FULL || !p.res32 || p.mode == 1 || i >= UPW_PREF || (c.abl & 2)) return;
                 const int im = item >> c.nsl_log2, ns = item & (c.nslices - 1);
                 const int uu = unit_of(i), j = uu >> c.nb32_log2, b = uu & (nb32 - 1);
                 const int m = (im * J + j) * MTILE + q * 32 + lane;
@@ -383,7 +392,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                         // validity only (no s2d / scatter targets needed)
                         const uint32_t bq = div_by_magic((uint32_t)m, g.magS, g.shS), r = (uint32_t)m - bq * (uint32_t)g.S;
                         const uint32_t y = div_by_magic(r, g.magW, g.shW), x = r - y * (uint32_t)g.Wp;
-                        const bool valid = m < g.M && (int)y < g.H && (int)x < g.W;
+                        const bool valid = m < g.M && (int)y < g.H && (int)x < g.W && !(c.abl & 2);
                         tc_ld_wait16(r0);
                         tc_ld_wait16(r1);
                         if (valid) {
@@ -398,7 +407,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                             for (int k = 0; k < 4; ++k) dst[(size_t)k * Ptot] = pack8_half(v + 8 * k);
                         }
                     } else {
-                        const RowCtx rc = make_row_ctx(p, m);
+                        RowCtx rc = make_row_ctx(p, m);
+                        if (c.abl & 2) rc.valid = false;
                         tc_ld_wait16(r0);
                         tc_ld_wait16(r1);
 #pragma unroll
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
 #pragma unroll
                             for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
                         }
-                        if (p.res32 && p.mode == 0 && m < g.M) {
+                        if (p.res32 && p.mode == 0 && m < g.M && !(c.abl & 2)) {
                             if (i < UPW_PREF) {
 #pragma unroll
                                 for (int k = 0; k < 32; ++k) v[k] += add[EPI == EPI_FULL && i < UPW_PREF ? i : 0][k];
@@ -451,6 +461,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
 
 static int g_num_sms = 0;
 static int g_l2pf = 0;
+static int g_bstages = 6;
+static int g_abl = 0;
 
 // Optional per-launch timing of k_conv_umma with CUDA events on the launching stream (gd_profile_begin/end):
 // bench.py uses it to measure the dominant kernel's average duration live for the roofline line.
@@ -487,6 +499,8 @@ int conv_umma_init() {
     GD_CUDA_CHECK(cudaGetDevice(&dev));
     GD_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     if (const char* e = getenv("GDECONV_L2PF")) g_l2pf = atoi(e);
+    if (const char* e = getenv("GDECONV_ABL")) g_abl = atoi(e);
+    if (const char* e = getenv("GDECONV_BSTAGES")) { g_bstages = atoi(e); if (g_bstages < 2 || g_bstages > MAX_B_STAGES) g_bstages = 6; }
 #define GD_UMMA_ATTR(J, KK)                                                                                                        \
     GD_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma<J, KK, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX)); \
     GD_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma<J, KK, EPI_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX))
@@ -508,11 +522,12 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     c.b_total_bytes = p.ntaps * p.Kt * p.N * 2;
     c.b_resident = (size_t)c.b_total_bytes <= B_RESIDENT_MAX;
     c.b_stage_bytes = c.ncta * c.BK * 2;
-    c.b_stages = c.b_resident ? 0 : 6;
+    c.b_stages = c.b_resident ? 0 : g_bstages;
     const size_t b_region = c.b_resident ? (size_t)c.b_total_bytes : (size_t)c.b_stages * c.b_stage_bytes;
     // resident weights: <= 128 accumulator columns per item (2 epilogue units per warp, fine-grained A ring, good tail
     // balance); streamed weights: 256 columns so that every weight stage is reused by twice as many rows
     c.J = (c.b_resident ? 128 : ACC_STAGE_COLS) / c.ncta;
+    if (c.J > 4) c.J = 4;
     for (;; c.J >>= 1) {
         c.win_rows = MTILE * c.J + 2 * c.halo;
         c.a_stage_bytes = c.win_rows * c.BK * 2;
@@ -525,6 +540,7 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     const int tiles = (p.g.M + MTILE - 1) / MTILE;
     c.items_m = (tiles + c.J - 1) / c.J;
     c.l2pf = g_l2pf;
+    c.abl = g_abl;
     auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
     c.nsl_log2 = ilog2(c.nslices); c.nb32_log2 = ilog2(c.ncta / 32);
     if ((1 << c.nsl_log2) != c.nslices || (1 << c.nb32_log2) != c.ncta / 32) { set_error("conv_umma: N=%d must split into power-of-two slices", p.N); return GD_EUNSUPPORTED; }

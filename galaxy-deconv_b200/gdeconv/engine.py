@@ -16,7 +16,7 @@ from ._lib import check, lib
 
 STAMP = 48
 NPIX = STAMP * STAMP
-_DEFAULT_CHUNK = 512
+_DEFAULT_CHUNK = 8192      # stamps per pass through the layer graph: long kernels beat L2 residency (profiles/ablation_r01.md)
 
 
 def default_precision() -> str:
@@ -27,8 +27,12 @@ def default_precision() -> str:
     return p
 
 
-def max_chunk() -> int:
-    return int(os.environ.get('GDECONV_CHUNK', _DEFAULT_CHUNK))
+def max_chunk(arch=_lib.ARCH_G) -> int:
+    """Upper bound on the stamps per pass through the layer graph (env GDECONV_CHUNK).  Long kernels beat L2 residency on
+    this path (profiles/ablation_r01.md), so the default is large: 8192 stamps = 22 GB of workspace for path G,
+    4096 = 22 GB for the twice-as-wide path U."""
+    env = os.environ.get('GDECONV_CHUNK')
+    return int(env) if env else (_DEFAULT_CHUNK if arch == _lib.ARCH_G else _DEFAULT_CHUNK // 2)
 
 
 def launch_count() -> int:
@@ -77,14 +81,18 @@ _ws_lock = threading.Lock()
 _ws_cache = {}
 
 
-def _chunk_for(batch):
-    cap = max_chunk()
-    if batch >= cap:
-        return cap
-    c = 1
-    while c < batch:
-        c *= 2
-    return min(c, cap)
+def _chunk_for(batch, arch=_lib.ARCH_G):
+    """Workspace capacity for a batch: the batch is cut into the fewest chunks that respect the cap, of (nearly) equal
+    size -- a short ragged last chunk would waste whole waves of the persistent kernels."""
+    cap = max(1, max_chunk(arch))
+    n = max(1, -(-batch // cap))
+    per = -(-max(batch, 1) // n)
+    if per <= 256:                      # small batches: powers of two keep the number of distinct workspaces low
+        c = 1
+        while c < per:
+            c *= 2
+        return min(c, cap)
+    return min(-(-per // 256) * 256, max(cap, 256))
 
 
 def _workspace(device, arch, prec, chunk):
@@ -96,6 +104,10 @@ def _workspace(device, arch, prec, chunk):
         nbytes = int(lib.gd_workspace_bytes(arch, prec, chunk))
         if nbytes == 0:
             raise RuntimeError('gd_workspace_bytes rejected the configuration')
+        # at most two workspaces per (device, arch, precision): drop the oldest before allocating a third
+        same = [k for k in _ws_cache if k[:3] == key[:3]]
+        for k in same[:-1] if len(same) >= 2 else []:
+            del _ws_cache[k]
         buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         check(lib.gd_workspace_init(_ptr(buf), nbytes, arch, prec, chunk, _stream(device)))
         _ws_cache[key] = (buf, nbytes)
@@ -174,7 +186,7 @@ class AdmmEngine:
         n_rho = self.n_iters if self.arch == _lib.ARCH_G else 2 * self.n_iters
         with torch.cuda.device(dev):
             w = self.weights(dev, precision)
-            ws, nbytes = _workspace(dev, self.arch, _lib.PRECISIONS[precision], _chunk_for(B))
+            ws, nbytes = _workspace(dev, self.arch, _lib.PRECISIONS[precision], _chunk_for(B, self.arch))
             out = torch.empty_like(y)
             rho = torch.empty(B, n_rho, device=dev) if want_rho else None
             ana = None
@@ -191,7 +203,7 @@ class AdmmEngine:
         precision = precision or default_precision()
         with torch.cuda.device(dev):
             w = self.weights(dev, precision)
-            ws, nbytes = _workspace(dev, self.arch, _lib.PRECISIONS[precision], _chunk_for(x.shape[0]))
+            ws, nbytes = _workspace(dev, self.arch, _lib.PRECISIONS[precision], _chunk_for(x.shape[0], self.arch))
             out = torch.empty_like(x)
             check(lib.gd_resunet_forward(w.handle, _ptr(x), _ptr(out), x.shape[0], _ptr(ws), nbytes, _stream(dev)))
         return out

@@ -84,7 +84,8 @@ def test_unsupported_configurations_raise():
 
 def test_host_helpers():
     from gdeconv import engine
-    assert engine._chunk_for(1) == 1 and engine._chunk_for(3) == 4 and engine._chunk_for(10 ** 6) == engine.max_chunk()
+    assert engine._chunk_for(1) == 1 and engine._chunk_for(3) == 4 and engine._chunk_for(10 ** 6) <= engine.max_chunk()
+    assert engine._chunk_for(10000) == 5120            # two balanced chunks of 5000, rounded up to a multiple of 256
     a = engine._alpha_vector(torch.full((1, 1, 1, 1), 2.5), 3, torch.device('cpu'))
     assert a.shape == (3,) and a.is_contiguous() and float(a[2]) == 2.5
     with pytest.raises(ValueError):
