@@ -258,7 +258,7 @@ extern "C" int gd_pack_weights(int arch, int n_iters, const GdTensorDesc* tensor
                 std::vector<float> w((size_t)Co * Ci * 9 + Co);
                 for (int co = 0; co < Co; ++co) {
                     const float sc = t[2]->data[co] / sqrtf(t[5]->data[co] + 1e-5f);      // nn.BatchNorm2d eps
-                    for (int i = 0; i < Ci * 9; ++i) w[(size_t)co * Ci * 9 + i] = t[0]->data[(size_t)co * Ci * 9 + i] * sc;
+                    for (int i = 0; i < Ci * 9; ++i) w[(size_t)i * Co + co] = t[0]->data[(size_t)co * Ci * 9 + i] * sc;   // [ci][tap][co]
                     w[(size_t)Co * Ci * 9 + co] = (t[1]->data[co] - t[4]->data[co]) * sc + t[3]->data[co];
                 }
                 slot((const void**)&W.sub.conv[2 * s + j], pack_f32(bl, w.data(), w.size()));

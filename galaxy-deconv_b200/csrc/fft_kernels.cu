@@ -209,6 +209,7 @@ __device__ __forceinline__ float lap_quirk_abs2(int k1, int k2, const float2* tw
 }
 
 constexpr size_t SOLVER_SMEM = (size_t)(ZU + 2 * SU + 48) * sizeof(float2) + (size_t)2 * NPIX * sizeof(float) + 64;
+constexpr size_t SOLVER_SMEM_LIGHT = (size_t)(ZU + 2 * SU + 48) * sizeof(float2) + 64;   // Wiener / Tikhonov / conv_fft: no x, y copies -> 7 CTAs per SM
 
 // kind: GD_SOLVER_* ; one CTA per stamp
 __global__ void __launch_bounds__(U_THREADS) k_solver(int kind, int n_iters, float lam, const float* __restrict__ y,
@@ -574,13 +575,13 @@ int launch_fill_rho(const float* src, int n_rho, float* rho, int batch, cudaStre
 int launch_solver(int kind, int n_iters, float lam, const float* y, const float* psf, const float* alpha, float* out,
                   int batch, cudaStream_t st) {
     if (batch <= 0) return GD_OK;
-    k_solver<<<batch, U_THREADS, SOLVER_SMEM, st>>>(kind, n_iters, lam, y, psf, alpha, out);
+    k_solver<<<batch, U_THREADS, kind == 0 ? SOLVER_SMEM : SOLVER_SMEM_LIGHT, st>>>(kind, n_iters, lam, y, psf, alpha, out);
     GD_LAUNCHED();
     return GD_OK;
 }
 int launch_conv_fft(const float* x, const float* psf, float* out, int adjoint, int batch, cudaStream_t st) {
     if (batch <= 0) return GD_OK;
-    k_conv_fft<<<batch, U_THREADS, SOLVER_SMEM, st>>>(x, psf, out, adjoint);
+    k_conv_fft<<<batch, U_THREADS, SOLVER_SMEM_LIGHT, st>>>(x, psf, out, adjoint);
     GD_LAUNCHED();
     return GD_OK;
 }

@@ -15,9 +15,14 @@ constexpr int SP128 = 66;
 constexpr int SN_THREADS = 256;
 constexpr int SN_Z = 24 * 128;                 // float2
 constexpr int SN_S = 128 * SP128;              // float2
-constexpr int SN_BUFB = 4 * 64 * 64;           // floats
+// conv-phase buffers: feature maps are stored with a one-pixel zero border, [C][H+2][H+2], so the 3x3 taps need no bounds
+// checks.  R0 (the FFT's Z+S region, 92 KB) and R1 (70 KB) ping-pong; the pooled maps (<= 4*34*34 floats) live in R2.
+constexpr int SN_MAP_MAX = 4 * 66 * 66;        // floats: largest padded map (4 channels at 64x64)
+constexpr int SN_POOL_MAX = 4 * 34 * 34;       // floats: largest pooled (conv-input) map: 4x34^2 = 4624 >= 1x66^2, 8x18^2, 16x10^2
 constexpr int SN_WMAX = 16 * 16 * 9 + 16;      // floats
-constexpr size_t SN_SMEM = (size_t)(SN_Z + SN_S + 128) * sizeof(float2) + (size_t)(SN_BUFB + SN_WMAX + 64 + 64) * sizeof(float);
+constexpr size_t SN_R0 = (size_t)(SN_Z + SN_S) * sizeof(float2);
+static_assert(SN_R0 >= (size_t)SN_MAP_MAX * sizeof(float), "R0 must hold the largest padded map");
+constexpr size_t SN_SMEM = SN_R0 + 128 * sizeof(float2) + (size_t)(SN_MAP_MAX + SN_POOL_MAX + SN_WMAX + 1088 + 64 + 64) * sizeof(float);
 
 __device__ __forceinline__ float abs2(float2 a) { return a.x * a.x + a.y * a.y; }
 
@@ -27,60 +32,76 @@ __device__ __forceinline__ float hth128(const float2* S, int k1, int k2) {
     return abs2(S[F128::L::slot(k1) * SP128 + k2]);
 }
 
-// out[co][y][x] = relu(b[co] + sum_ci sum_tap w[co][ci][tap] in[ci][y+dy][x+dx]), zero padding
+__device__ __forceinline__ void zero_fill(float* buf, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) buf[i] = 0.f;
+}
+
+// 3x3 conv + folded BN + ReLU on zero-bordered maps.  in [Cin][H+2][H+2] -> out [Cout][H+2][H+2] (border pre-zeroed).
+// One work item = one pixel x 4 output channels: per (ci, tap) one input LDS, one broadcast LDS.128 of 4 weights, 4 FMAs.
+// wg: [Cin][9][Cout] weights followed by [Cout] biases (pack.cu: api.cu::gd_pack_weights).
 __device__ void conv3x3_relu(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ wg,
                              float* wsm, int Cin, int Cout, int H) {
     const int nw = Cout * Cin * 9 + Cout;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) wsm[i] = wg[i];
+    const int Hp = H + 2, HW = H * H, ngrp = Cout >> 2;
     __syncthreads();
-    const int HW = H * H;
     const float* bias = wsm + Cout * Cin * 9;
-    for (int item = threadIdx.x; item < Cout * HW; item += blockDim.x) {
-        int co = item / HW, p = item - co * HW, y = p / H, x = p - y * H;
-        float acc = bias[co];
-        const float* w = wsm + co * Cin * 9;
+    for (int item = threadIdx.x; item < HW * ngrp; item += blockDim.x) {
+        const int cg = item / HW, p = item - cg * HW, y = p / H, x = p - y * H;
+        float a0 = bias[4 * cg], a1 = bias[4 * cg + 1], a2 = bias[4 * cg + 2], a3 = bias[4 * cg + 3];
+        const float* ip = in + y * Hp + x;                    // top-left tap of pixel (y, x) in the padded map
+        const float* wp = wsm + 4 * cg;
         for (int ci = 0; ci < Cin; ++ci) {
-            const float* ip = in + ci * HW;
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-                int yy = y + dy;
-                if (yy < 0 || yy >= H) continue;
-#pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    int xx = x + dx;
-                    if (xx < 0 || xx >= H) continue;
-                    acc = fmaf(w[ci * 9 + (dy + 1) * 3 + dx + 1], ip[yy * H + xx], acc);
-                }
+            for (int t = 0; t < 9; ++t) {
+                const float v = ip[(t / 3) * Hp + (t % 3)];
+                const float4 w = *reinterpret_cast<const float4*>(wp + (ci * 9 + t) * Cout);
+                a0 = fmaf(v, w.x, a0); a1 = fmaf(v, w.y, a1); a2 = fmaf(v, w.z, a2); a3 = fmaf(v, w.w, a3);
             }
+            ip += Hp * Hp;
         }
-        out[item] = fmaxf(acc, 0.f);
+        float* op = out + (4 * cg) * Hp * Hp + (y + 1) * Hp + (x + 1);
+        op[0] = fmaxf(a0, 0.f); op[Hp * Hp] = fmaxf(a1, 0.f); op[2 * Hp * Hp] = fmaxf(a2, 0.f); op[3 * Hp * Hp] = fmaxf(a3, 0.f);
     }
     __syncthreads();
 }
 
+// MaxPool2d(2): in [C][H+2][H+2] (bordered) -> out [C][H/2+2][H/2+2] (border pre-zeroed)
 __device__ void maxpool2(const float* __restrict__ in, float* __restrict__ out, int C, int H) {
-    const int Ho = H / 2;
+    const int Ho = H / 2, Hp = H + 2, Hop = Ho + 2;
     for (int item = threadIdx.x; item < C * Ho * Ho; item += blockDim.x) {
         int c = item / (Ho * Ho), p = item - c * Ho * Ho, y = p / Ho, x = p - y * Ho;
-        const float* ip = in + c * H * H + (2 * y) * H + 2 * x;
-        out[item] = fmaxf(fmaxf(ip[0], ip[1]), fmaxf(ip[H], ip[H + 1]));
+        const float* ip = in + c * Hp * Hp + (2 * y + 1) * Hp + 2 * x + 1;
+        out[c * Hop * Hop + (y + 1) * Hop + x + 1] = fmaxf(fmaxf(ip[0], ip[1]), fmaxf(ip[Hp], ip[Hp + 1]));
     }
     __syncthreads();
 }
 
-// out[o] = act(b[o] + sum_i w[o][i] in[i]);  one warp per output, lanes stride the inputs
+// out[o] = act(b[o] + sum_i w[o][i] in[i]);  each warp owns n_out/nwarps outputs and keeps up to 8 of them in flight per
+// pass over the inputs (8 independent coalesced weight loads per lane and step)
 __device__ void linear(const float* __restrict__ w, const float* __restrict__ bvec, const float* in, float* out, int n_in,
                        int n_out, int act) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int o = warp; o < n_out; o += nwarps) {
-        float s = 0.f;
-        for (int i = lane; i < n_in; i += 32) s = fmaf(w[(size_t)o * n_in + i], in[i], s);
-        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (lane == 0) {
-            s += bvec[o];
-            if (act == 1) s = fmaxf(s, 0.f);
-            else if (act == 2) s = (s > 20.f ? s : log1pf(expf(s))) + 1e-6f;       // nn.Softplus() + 1e-6 (:70)
-            out[o] = s;
+    for (int o0 = warp * 8; o0 < n_out; o0 += nwarps * 8) {
+        float s[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] = 0.f;
+        for (int i = lane; i < n_in; i += 32) {
+            const float f = in[i];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (o0 + k < n_out) s[k] = fmaf(__ldg(w + (size_t)(o0 + k) * n_in + i), f, s[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = s[k];
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0 && o0 + k < n_out) {
+                v += bvec[o0 + k];
+                if (act == 1) v = fmaxf(v, 0.f);
+                else if (act == 2) v = (v > 20.f ? v : log1pf(expf(v))) + 1e-6f;       // nn.Softplus() + 1e-6 (:70)
+                out[o0 + k] = v;
+            }
         }
     }
     __syncthreads();
@@ -92,12 +113,13 @@ __global__ void __launch_bounds__(SN_THREADS) k_subnet(SubnetParams P, const flo
     float2* Z = reinterpret_cast<float2*>(smem_raw);
     float2* S = Z + SN_Z;
     float2* tw = S + SN_S;
-    float* bufB = reinterpret_cast<float*>(tw + 128);
-    float* wsm = bufB + SN_BUFB;
-    float* h1 = wsm + SN_WMAX;
+    float* R0 = reinterpret_cast<float*>(smem_raw);          // aliases Z+S once the spectrum has been pooled
+    float* R1 = reinterpret_cast<float*>(tw + 128);
+    float* R2 = R1 + SN_MAP_MAX;
+    float* wsm = R2 + SN_POOL_MAX;
+    float* feat = wsm + SN_WMAX;                             // 1025 features
+    float* h1 = feat + 1088;
     float* h2 = h1 + 64;
-    float* bufP = reinterpret_cast<float*>(Z);     // pooled maps / features (<= 4096 floats, fits the 24.5 KB of Z)
-    float* bufA = reinterpret_cast<float*>(S);     // 67.6 KB >= 4*64*64 floats
     const int b = blockIdx.x;
     const float* kb = psf + (size_t)b * NPIX;
     fill_twiddles<128>(tw);
@@ -106,25 +128,39 @@ __global__ void __launch_bounds__(SN_THREADS) k_subnet(SubnetParams P, const flo
         Z[j * 128 + c] = make_float2(kb[(2 * j) * 48 + c], kb[(2 * j + 1) * 48 + c]);
     }
     fwd2d<F128, SP128>(Z, S, tw);
-    // MaxPool2d(2) of |H|^2 in natural frequency order -> bufP [64][64]
+    // MaxPool2d(2) of |H|^2 in natural frequency order -> R2 [1][66][66] (zero border)
+    zero_fill(R2, 66 * 66);
+    __syncthreads();
     for (int item = threadIdx.x; item < 64 * 64; item += blockDim.x) {
         int i = item >> 6, j = item & 63;
-        float m = fmaxf(fmaxf(hth128(S, 2 * i, 2 * j), hth128(S, 2 * i, 2 * j + 1)),
-                        fmaxf(hth128(S, 2 * i + 1, 2 * j), hth128(S, 2 * i + 1, 2 * j + 1)));
-        bufP[item] = m;
+        R2[(i + 1) * 66 + j + 1] = fmaxf(fmaxf(hth128(S, 2 * i, 2 * j), hth128(S, 2 * i, 2 * j + 1)),
+                                         fmaxf(hth128(S, 2 * i + 1, 2 * j), hth128(S, 2 * i + 1, 2 * j + 1)));
     }
     __syncthreads();
     const int cin[4] = {1, 4, 8, 16}, cout[4] = {4, 8, 16, 16};
     int H = 64;
     for (int s = 0; s < 4; ++s) {
-        conv3x3_relu(bufP, bufA, P.conv[2 * s], wsm, cin[s], cout[s], H);
-        conv3x3_relu(bufA, bufB, P.conv[2 * s + 1], wsm, cout[s], cout[s], H);
-        if (s < 3) { maxpool2(bufB, bufP, cout[s], H); H >>= 1; }
+        const int np = cout[s] * (H + 2) * (H + 2);
+        zero_fill(R0, np);
+        zero_fill(R1, np);
+        __syncthreads();
+        conv3x3_relu(R2, R0, P.conv[2 * s], wsm, cin[s], cout[s], H);
+        conv3x3_relu(R0, R1, P.conv[2 * s + 1], wsm, cout[s], cout[s], H);
+        if (s < 3) {
+            zero_fill(R2, cout[s] * (H / 2 + 2) * (H / 2 + 2));
+            __syncthreads();
+            maxpool2(R1, R2, cout[s], H);
+            H >>= 1;
+        }
     }
-    // features: bufB [16][8][8] flattened channel-major (x.view(N,1,1024), :68) followed by alpha
-    if (threadIdx.x == 0) bufB[1024] = alpha[b];
+    // features: [16][8][8] flattened channel-major (x.view(N,1,1024), :68) followed by alpha
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        int c = i >> 6, y = (i >> 3) & 7, x = i & 7;
+        feat[i] = R1[c * 100 + (y + 1) * 10 + x + 1];
+    }
+    if (threadIdx.x == 0) feat[1024] = alpha[b];
     __syncthreads();
-    linear(P.l1w, P.l1b, bufB, h1, 1025, 64, 1);
+    linear(P.l1w, P.l1b, feat, h1, 1025, 64, 1);
     linear(P.l2w, P.l2b, h1, h2, 64, 64, 1);
     linear(P.l3w, P.l3b, h2, rho + (size_t)b * P.n_out, 64, P.n_out, 2);
 }
