@@ -228,7 +228,16 @@ def main():
         lib.gd_profile_end(C.byref(ms_k), C.byref(fl_k), C.byref(n_k))
         if ms_k.value > 0:
             ach = fl_k.value / (ms_k.value * 1e-3) / 1e12
-            roof = dict(bound='tensor', achieved=ach, peak=P['tensor_sustained'], unit='TFLOP/s', frac=ach / P['tensor_sustained'], traffic=None,
+            traffic, traffic_note = None, 'no ncu capture found under profiles/'
+            try:        # DRAM bytes per launch from the committed ncu capture of the same kernel (per launch, like `achieved`)
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic_r01.json')))
+                per_chunk = engine._chunk_for(hi - lo)
+                traffic = tj['avg_traffic_bytes_per_launch'] * min(per_chunk, hi - lo) / tj['stamps_per_launch']
+                traffic_note = 'ncu dram__bytes_read+write per k_conv_umma launch (profiles/roofline_traffic_r01.json), scaled by stamps per launch'
+            except Exception:
+                pass
+            roof = dict(bound='tensor', achieved=ach, peak=P['tensor_sustained'], unit='TFLOP/s', frac=ach / P['tensor_sustained'], traffic=traffic,
+                        traffic_note=traffic_note,
                         kernel='k_conv_umma', launches_per_step=int(n_k.value), avg_launch_us=ms_k.value * 1e3 / max(1, n_k.value),
                         kernel_share_of_step=ms_k.value / ms_step, flops_per_launch_avg=fl_k.value / max(1, n_k.value),
                         peak_source=P['source'] + ', sustained bf16 (kernel timed inside a long step); burst = %.1f' % P['tensor_burst'])

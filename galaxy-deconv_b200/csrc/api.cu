@@ -173,6 +173,7 @@ static int init_once(int device) {
     GD_TRY(fft_kernels_init());
     GD_TRY(subnet_init());
     GD_TRY(conv_umma_init());
+    GD_TRY(conv_chain_init());
     done.fetch_or(1u << device);
     return GD_OK;
 }
@@ -336,6 +337,7 @@ struct Ws {
     // ResUNet activations
     float *skip32[4], *p32a[4], *p32b[4];
     void *a16[4], *t16[4], *d16[4];
+    unsigned int* chain_flags;                 // per-(layer, item) completion counters of the layer-chained kernel
 };
 
 static Ws ws_layout(unsigned char* base, int arch, int prec, int chunk) {
@@ -368,6 +370,7 @@ static Ws ws_layout(unsigned char* base, int arch, int prec, int chunk) {
         w.t16[L] = take(n * es);
         if (L > 0) w.d16[L] = take((size_t)2 * n * es);        // 4*C_{L-1} = 2*C_L channels
     }
+    w.chain_flags = (unsigned int*)take(chain_flag_words(w.g[0].Ptot) * sizeof(unsigned int));
     w.total = off;
     return w;
 }
@@ -420,6 +423,15 @@ static int run_conv(const ConvParams& p, int prec, cudaStream_t st) {
 // Sub-chunking: the wide, shallow levels 0-1 (48x48 and 24x24, ~1.2 MB of activations per stamp) are walked
 // sub-chunk by sub-chunk so that a sub-chunk's working set stays in the 126 MB L2 across consecutive layers, while
 // the narrow, deep levels 2-3 run over the whole chunk at once (enough 128-row tiles to fill 148 SMs).
+static int g_chain = -1;
+static int chain_mode() {
+    if (g_chain < 0) {
+        const char* e = getenv("GDECONV_CHAIN");
+        g_chain = e ? atoi(e) : 0;               // 1: layer-chained launches at the 32- and 64-channel levels (conv_chain.cu);
+                                                 // off by default: measured 7 % slower than one launch per layer (profiles/)
+    }
+    return g_chain;
+}
 static int g_subchunk = 0;
 static int subchunk_size() {
     if (!g_subchunk) {
@@ -443,21 +455,39 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         p.N = C[0]; p.out32 = ws.skip32[0]; p.out16 = ws.a16[0];
         GD_TRY(launch_head(t, W->head, C[0], p, nb, prec, st));
     }
-    // one ResBlock (resnet_basicblock.py:69-71) on stamps [s0, s0+n): stream + conv(relu(conv(stream)))
+    // one ResBlock (resnet_basicblock.py:69-71) on stamps [s0, s0+n): stream + conv(relu(conv(stream))) -> two layers
+    auto rb_params = [&](int L, int s0, int n, const void* const* w2, const float* res, const float* skip, float* out32,
+                         void* out16, void* s2d, ConvParams* out) {
+        out[0] = conv3(g[L], n, C[L], at(ws.a16[L], L, s0), w2[0], 1);
+        out[0].out16 = at(ws.t16[L], L, s0);
+        out[1] = conv3(g[L], n, C[L], at(ws.t16[L], L, s0), w2[1], 0);
+        out[1].res32 = (const float*)at(res, L, s0); out[1].skip32 = (const float*)at(skip, L, s0);
+        out[1].out32 = (float*)at(out32, L, s0); out[1].out16 = at(out16, L, s0);
+        if (s2d) { out[1].s2d = at(s2d, L + 1, s0); out[1].gc = g[L + 1]; out[1].gc.M = n * g[L + 1].S; }
+    };
     auto resblock = [&](int L, int s0, int n, const void* const* w2, const float* res, const float* skip, float* out32,
                         void* out16, void* s2d) -> int {
-        ConvParams p1 = conv3(g[L], n, C[L], at(ws.a16[L], L, s0), w2[0], 1);
-        p1.out16 = at(ws.t16[L], L, s0);
-        GD_TRY(run_conv(p1, prec, st));
-        ConvParams p2 = conv3(g[L], n, C[L], at(ws.t16[L], L, s0), w2[1], 0);
-        p2.res32 = (const float*)at(res, L, s0); p2.skip32 = (const float*)at(skip, L, s0);
-        p2.out32 = (float*)at(out32, L, s0); p2.out16 = at(out16, L, s0);
-        if (s2d) { p2.s2d = at(s2d, L + 1, s0); p2.gc = g[L + 1]; p2.gc.M = n * g[L + 1].S; }
-        return run_conv(p2, prec, st);
+        ConvParams p[2];
+        rb_params(L, s0, n, w2, res, skip, out32, out16, s2d, p);
+        if (prec == PREC_FP16_UMMA && chain_mode() && C[L] == 64) return launch_conv_chain(p, 2, ws.chain_flags, st);
+        GD_TRY(run_conv(p[0], prec, st));
+        return run_conv(p[1], prec, st);
+    };
+    // two consecutive ResBlocks of one level: one chained launch when all four layers' weights fit in shared memory
+    auto resblock_pair = [&](int L, int s0, int n, const void* const* wa, const void* const* wb, const float* res_a, float* out32_a,
+                             void* out16_a, const float* res_b, const float* skip_b, float* out32_b, void* out16_b, void* s2d_b) -> int {
+        if (prec == PREC_FP16_UMMA && chain_mode() && C[L] == 32) {
+            ConvParams p[4];
+            rb_params(L, s0, n, wa, res_a, nullptr, out32_a, out16_a, nullptr, p);
+            rb_params(L, s0, n, wb, res_b, skip_b, out32_b, out16_b, s2d_b, p + 2);
+            return launch_conv_chain(p, 4, ws.chain_flags, st);
+        }
+        GD_TRY(resblock(L, s0, n, wa, res_a, nullptr, out32_a, out16_a, nullptr));
+        return resblock(L, s0, n, wb, res_b, skip_b, out32_b, out16_b, s2d_b);
     };
     auto down_stage = [&](int L, int s0, int n) -> int {          // m_down{L+1} (ResUNet.py:32-34)
-        GD_TRY(resblock(L, s0, n, W->down_rb[L][0], ws.skip32[L], nullptr, ws.p32a[L], ws.a16[L], nullptr));
-        GD_TRY(resblock(L, s0, n, W->down_rb[L][1], ws.p32a[L], nullptr, nullptr, nullptr, ws.d16[L + 1]));
+        GD_TRY(resblock_pair(L, s0, n, W->down_rb[L][0], W->down_rb[L][1], ws.skip32[L], ws.p32a[L], ws.a16[L], ws.p32a[L], nullptr,
+                             nullptr, nullptr, ws.d16[L + 1]));
         ConvParams p = conv_base(g[L + 1], n);         // k2s2 strided conv as a 1-tap GEMM on the space-to-depth copy
         p.ntaps = 1; p.off[0] = 0; p.Kt = 4 * C[L]; p.N = C[L + 1]; p.a = at(ws.d16[L + 1], L + 1, s0); p.w = W->down[L];
         p.out32 = (float*)at(ws.skip32[L + 1], L + 1, s0); p.out16 = at(ws.a16[L + 1], L + 1, s0);
@@ -469,9 +499,10 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         p.mode = 1; p.Cf = C[L]; p.Cf_log2 = 0; while ((1 << p.Cf_log2) < p.Cf) ++p.Cf_log2; p.gf = g[L]; p.gf.M = n * g[L].S;
         p.out32 = (float*)at(ws.p32a[L], L, s0); p.out16 = at(ws.a16[L], L, s0);
         GD_TRY(run_conv(p, prec, st));
-        GD_TRY(resblock(L, s0, n, W->up_rb[L][0], ws.p32a[L], nullptr, ws.p32b[L], ws.a16[L], nullptr));
-        if (L > 0) return resblock(L, s0, n, W->up_rb[L][1], ws.p32b[L], ws.skip32[L], nullptr, ws.a16[L], nullptr);
-        return resblock(L, s0, n, W->up_rb[L][1], ws.p32b[L], ws.skip32[L], ws.p32a[L], nullptr, nullptr);
+        if (L > 0) return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L],
+                                        ws.skip32[L], nullptr, ws.a16[L], nullptr);
+        return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L], ws.skip32[L],
+                             ws.p32a[L], nullptr, nullptr);
     };
     const int sub = subchunk_size();
     for (int s0 = 0; s0 < nb; s0 += sub) {

@@ -9,6 +9,9 @@ namespace gd {
 int fft_kernels_init();
 int subnet_init();
 int conv_umma_init();
+int conv_chain_init();
+size_t chain_flag_words(int max_rows);
+int launch_conv_chain(const ConvParams* layers, int nl, unsigned int* flags, cudaStream_t st);
 void conv_profile_begin();
 int conv_profile_end(double* ms_total, double* flops_total, unsigned long long* launches);
 
