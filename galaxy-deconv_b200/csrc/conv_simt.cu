@@ -103,31 +103,41 @@ __global__ void __launch_bounds__(128) k_head(const float* __restrict__ t, const
 }
 
 // tail: x32 [C0/4][Ptot][4] fp32 -> z [B][48*48] fp32, times the per-stamp power-of-two scale.
-__global__ void __launch_bounds__(128) k_tail(const float* __restrict__ x32, const float* __restrict__ w, int C0, Geom g,
-                                              const float* __restrict__ tscale, float* __restrict__ z, int batch) {
-    extern __shared__ float wsm[];           // 9*C0
+// Works in the padded-linear row space (the halo rows of the stream are zero, so there are no bounds checks): a CTA
+// stages the window rows [m0 - Wp - 1, m0 + TAIL_ROWS + Wp + 1) of all C0/4 planes in shared memory with coalesced
+// 16-byte loads (each element leaves L2 once instead of nine times through L1), then every thread reduces the 9 taps x
+// C0 channels of its row from shared memory (conflict-free LDS.128) and writes its pixel if the row is a real one.
+constexpr int TAIL_ROWS = 256;
+__global__ void __launch_bounds__(TAIL_ROWS) k_tail(const float* __restrict__ x32, const float* __restrict__ w, int C0, Geom g,
+                                                    const float* __restrict__ tscale, float* __restrict__ z, int batch) {
+    extern __shared__ __align__(16) float tsm[];          // [9*C0 weights][C0/4 planes][win rows][4]
+    float* wsm = tsm;
+    const int halo = g.Wp + 1, win = TAIL_ROWS + 2 * halo, planes = C0 / 4;
+    float4* xs = reinterpret_cast<float4*>(tsm + 9 * C0);
     for (int i = threadIdx.x; i < 9 * C0; i += blockDim.x) wsm[i] = w[i];
+    const int m0 = blockIdx.x * TAIL_ROWS;
+    const float4* src = reinterpret_cast<const float4*>(x32) + (g.base0 + m0 - halo);
+    for (int i = threadIdx.x; i < planes * win; i += blockDim.x) {
+        const int pl = i / win, r = i - pl * win;
+        xs[i] = __ldg(src + (size_t)pl * g.Ptot + r);
+    }
     __syncthreads();
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= batch * NPIX) return;
-    int b = idx / NPIX, r = idx - b * NPIX, y = r / STAMP, x = r - y * STAMP;
-    int row = g.base0 + b * g.S + y * g.Wp + x;
+    const int m = m0 + threadIdx.x;
+    if (m >= g.M) return;
+    const int b = (int)div_by_magic((uint32_t)m, g.magS, g.shS), r = m - b * g.S;
+    const int y = (int)div_by_magic((uint32_t)r, g.magW, g.shW), x = r - y * g.Wp;
+    if (y >= g.H || x >= g.W) return;
     float s = 0.f;
+    const float4* row = xs + halo + threadIdx.x;
+    for (int pl = 0; pl < planes; ++pl) {
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            int yy = y + dy, xx = x + dx;
-            if (yy < 0 || yy >= STAMP || xx < 0 || xx >= STAMP) continue;
-            const float* wp = wsm + ((dy + 1) * 3 + dx + 1) * C0;
-            const float* xp = x32 + (size_t)(row + dy * g.Wp + dx) * 4;
-            for (int c4 = 0; c4 < C0 / 4; ++c4) {
-                float4 v = *reinterpret_cast<const float4*>(xp + (size_t)c4 * g.Ptot * 4);
-                s = fmaf(v.x, wp[4 * c4], s); s = fmaf(v.y, wp[4 * c4 + 1], s);
-                s = fmaf(v.z, wp[4 * c4 + 2], s); s = fmaf(v.w, wp[4 * c4 + 3], s);
-            }
+        for (int t = 0; t < 9; ++t) {
+            const float4 v = row[pl * win + (t / 3 - 1) * g.Wp + (t % 3 - 1)];
+            const float4 wv = *reinterpret_cast<const float4*>(wsm + t * C0 + 4 * pl);
+            s = fmaf(v.x, wv.x, s); s = fmaf(v.y, wv.y, s); s = fmaf(v.z, wv.z, s); s = fmaf(v.w, wv.w, s);
         }
-    z[idx] = s * tscale[b];
+    }
+    z[(size_t)b * NPIX + y * STAMP + x] = s * tscale[b];
 }
 
 // ---- host launchers ----
@@ -151,9 +161,14 @@ int launch_head(const float* t, const float* w, int C0, const ConvParams& p, int
 
 int launch_tail(const float* x32, const float* w, int C0, const Geom& g, const float* tscale, float* z, int batch,
                 cudaStream_t st) {
-    int n = batch * NPIX, blocks = (n + 127) / 128;
-    if (n <= 0) return GD_OK;
-    k_tail<<<blocks, 128, 9 * C0 * sizeof(float), st>>>(x32, w, C0, g, tscale, z, batch);
+    if (batch <= 0) return GD_OK;
+    Geom gg = g;
+    gg.M = batch * g.S;
+    const int blocks = (gg.M + TAIL_ROWS - 1) / TAIL_ROWS;
+    const size_t smem = (size_t)9 * C0 * sizeof(float) + (size_t)(C0 / 4) * (TAIL_ROWS + 2 * (g.Wp + 1)) * 16;
+    static bool attr_set = false;
+    if (!attr_set) { GD_CUDA_CHECK(cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set = true; }
+    k_tail<<<blocks, TAIL_ROWS, smem, st>>>(x32, w, C0, gg, tscale, z, batch);
     GD_LAUNCHED();
     return GD_OK;
 }

@@ -212,9 +212,11 @@ constexpr size_t SOLVER_SMEM = (size_t)(ZU + 2 * SU + 48) * sizeof(float2) + (si
 constexpr size_t SOLVER_SMEM_LIGHT = (size_t)(ZU + 2 * SU + 48) * sizeof(float2) + 64;   // Wiener / Tikhonov / conv_fft: no x, y copies -> 7 CTAs per SM
 
 // kind: GD_SOLVER_* ; one CTA per stamp
-__global__ void __launch_bounds__(U_THREADS) k_solver(int kind, int n_iters, float lam, const float* __restrict__ y,
+__global__ void __launch_bounds__(U_THREADS) k_solver(int kind_flags, int n_iters, float lam, const float* __restrict__ y,
                                                       const float* __restrict__ psf, const float* __restrict__ alpha,
                                                       float* __restrict__ out) {
+    const int kind = kind_flags & 0xff;
+    const bool clamp_y = (kind_flags & 0x100) != 0;       // Tikhonet clamps y before its Tikhonov step (models/Tikhonet.py:43)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* Z = reinterpret_cast<float2*>(smem_raw);
     float2* S = Z + ZU;
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(U_THREADS) k_solver(int kind, int n_iters, flo
     }
     const float a = alpha[b];
     // Wiener: fftn(y) un-clamped, un-scaled (models/Wiener.py:16-18); Tikhonov: fftn(y/alpha) (models/Tikhonet.py:20)
-    load_packed48(Z, y + o, kind == 1 ? 1.f : 1.0f / a, false);
+    load_packed48(Z, y + o, kind == 1 ? 1.f : 1.0f / a, clamp_y);
     fwd2d<FU48, SPU>(Z, S, tw);
     for (int q = threadIdx.x; q < FU_SPEC; q += blockDim.x) {
         int s1 = q / FU_NH, k2 = q - s1 * FU_NH, idx = s1 * SPU + k2;
@@ -575,7 +577,7 @@ int launch_fill_rho(const float* src, int n_rho, float* rho, int batch, cudaStre
 int launch_solver(int kind, int n_iters, float lam, const float* y, const float* psf, const float* alpha, float* out,
                   int batch, cudaStream_t st) {
     if (batch <= 0) return GD_OK;
-    k_solver<<<batch, U_THREADS, kind == 0 ? SOLVER_SMEM : SOLVER_SMEM_LIGHT, st>>>(kind, n_iters, lam, y, psf, alpha, out);
+    k_solver<<<batch, U_THREADS, (kind & 0xff) == 0 ? SOLVER_SMEM : SOLVER_SMEM_LIGHT, st>>>(kind, n_iters, lam, y, psf, alpha, out);
     GD_LAUNCHED();
     return GD_OK;
 }

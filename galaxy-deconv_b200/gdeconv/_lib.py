@@ -19,7 +19,8 @@ PRECISIONS = {'fp32_simt': PREC_FP32_SIMT, 'fp16_umma': PREC_FP16_UMMA, 'fp16_si
 #: every symbol include/gdeconv.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = ('gd_version', 'gd_last_error', 'gd_pack_weights', 'gd_free_weights', 'gd_workspace_bytes', 'gd_workspace_init',
            'gd_admm_forward', 'gd_resunet_forward', 'gd_subnet_forward', 'gd_fft_solver', 'gd_conv_fft', 'gd_moments_e',
-           'gd_launch_count', 'gd_debug_geom', 'gd_debug_tapgemm', 'gd_profile_begin', 'gd_profile_end')
+           'gd_launch_count', 'gd_debug_geom', 'gd_debug_tapgemm', 'gd_profile_begin', 'gd_profile_end', 'gd_pack_xdense', 'gd_free_xdense', 'gd_xdense_workspace_bytes',
+           'gd_xdense_forward', 'gd_tikhonet_forward')
 
 
 class GdTensorDesc(C.Structure):
@@ -48,6 +49,13 @@ def _load():
     lib.gd_conv_fft.argtypes = [vp, vp, vp, i, i, vp]
     lib.gd_moments_e.argtypes = [vp, vp, i, vp]
     lib.gd_profile_begin.restype = None
+    lib.gd_pack_xdense.argtypes = [C.POINTER(GdTensorDesc), i, C.c_char_p, i, C.POINTER(vp)]
+    lib.gd_free_xdense.argtypes = [vp]
+    lib.gd_free_xdense.restype = None
+    lib.gd_xdense_workspace_bytes.argtypes = [i]
+    lib.gd_xdense_workspace_bytes.restype = sz
+    lib.gd_xdense_forward.argtypes = [vp, vp, vp, i, vp, sz, i, vp]
+    lib.gd_tikhonet_forward.argtypes = [vp, i, f, vp, vp, vp, vp, i, vp, sz, i, vp]
     lib.gd_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.gd_debug_geom.argtypes = [i, i, C.POINTER(C.c_int * 7)]
     lib.gd_debug_tapgemm.argtypes = [i, i, i, i, i, i, i, vp, vp, vp, vp]

@@ -253,3 +253,93 @@ def moments_e(img):
     with torch.cuda.device(img.device):
         check(lib.gd_moments_e(_ptr(img), _ptr(e), img.shape[0], _stream(img.device)))
     return e
+
+
+# ---------------------------------------------------------------------------------------------------
+# XDenseUNet / Tikhonet (csrc/xdense.cu)
+# ---------------------------------------------------------------------------------------------------
+class _PackedX:
+    def __init__(self, handle):
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib.gd_free_xdense(self.handle)
+        except Exception:
+            pass
+
+
+_XD_CHUNK = 2048
+_xd_ws = {}
+
+
+def _xd_workspace(device, chunk):
+    key = (device.index, chunk)
+    hit = _xd_ws.get(key)
+    if hit is None:
+        for k in [k for k in _xd_ws if k[0] == device.index]:
+            del _xd_ws[k]
+        nbytes = int(lib.gd_xdense_workspace_bytes(chunk))
+        hit = (torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes)
+        _xd_ws[key] = hit
+    return hit
+
+
+class XDenseEngine:
+    """Packed XDenseUNet weights of a module (XDenseUNet itself: prefix '', Tikhonet: prefix 'denoiser.')."""
+
+    def __init__(self, module, prefix):
+        self._module, self._prefix, self._packed = module, prefix, {}
+
+    def _weights(self, device):
+        sd = self._module.state_dict(keep_vars=True)
+        sig = tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+        hit = self._packed.get(device.index)
+        if hit is None or hit[0] != sig:
+            names, arrays = [], []
+            for k, v in self._module.state_dict().items():
+                if torch.is_tensor(v) and v.dtype.is_floating_point and v.dim() <= 4:
+                    names.append(k.encode()); arrays.append(v.detach().to('cpu', torch.float32).contiguous())
+            descs = (_lib.GdTensorDesc * len(names))()
+            for i, (n, a) in enumerate(zip(names, arrays)):
+                descs[i].name, descs[i].data, descs[i].ndim = n, a.data_ptr(), a.dim()
+                for d in range(a.dim()):
+                    descs[i].shape[d] = a.shape[d]
+            out = C.c_void_p()
+            check(lib.gd_pack_xdense(descs, len(names), self._prefix.encode(), device.index, C.byref(out)))
+            hit = (sig, _PackedX(out))
+            self._packed[device.index] = hit
+        return hit[1]
+
+    @staticmethod
+    def _chunk(batch):
+        c = 1
+        while c < min(batch, _XD_CHUNK):
+            c *= 2
+        return c
+
+    def denoise(self, x):
+        x = require_cuda_stamps('x', x)
+        dev, B = x.device, x.shape[0]
+        with torch.cuda.device(dev):
+            w = self._weights(dev)
+            chunk = self._chunk(B)
+            ws, nbytes = _xd_workspace(dev, chunk)
+            out = torch.empty_like(x)
+            check(lib.gd_xdense_forward(w.handle, _ptr(x), _ptr(out), B, _ptr(ws), nbytes, chunk, _stream(dev)))
+        return out
+
+    def tikhonet(self, kind, lam, y, psf, alpha):
+        y = require_cuda_stamps('y', y)
+        dev, B = y.device, y.shape[0]
+        psf = require_cuda_stamps('psf', psf, B)
+        a = _alpha_vector(alpha, B, dev)
+        with torch.cuda.device(dev):
+            w = self._weights(dev)
+            chunk = self._chunk(B)
+            ws, nbytes = _xd_workspace(dev, chunk)
+            out = torch.empty_like(y)
+            check(lib.gd_tikhonet_forward(w.handle, kind, float(lam), _ptr(y), _ptr(psf), _ptr(a), _ptr(out), B, _ptr(ws), nbytes, chunk,
+                                          _stream(dev)))
+        return out

@@ -1,6 +1,6 @@
 """Tikhonov step on libgdeconv (reference: models/Tikhonet.py:8-31), including the 7-non-zero "Laplacian" that
-psf_to_otf makes of the 3x3 kernel.  The Tikhonet wrapper (:34-47) needs the XDenseUNet
-denoiser, which is outside the hot path of this round."""
+psf_to_otf makes of the 3x3 kernel, and the full Tikhonet model (:34-47) with the XDenseUNet
+denoiser (models/XDenseUNet.py, csrc/xdense.cu)."""
 import torch
 import torch.nn as nn
 
@@ -24,7 +24,19 @@ class Tikhonov(nn.Module):
 
 
 class Tikhonet(nn.Module):
+    """Tikhonov step + XDenseUNet denoiser (reference :34-47): clamp(y) -> Tikhonov(filter, lam=1) -> denoiser -> * alpha,
+    one C-ABI call (gd_tikhonet_forward).  `lam` is a plain tensor attribute exactly like the reference's (:39), so it is
+    not part of the state_dict; the committed Tikhonet_*/ShapeNet_* weight files load with all keys matched."""
+
     def __init__(self, filter='Identity'):
         super().__init__()
-        raise NotImplementedError('gdeconv: Tikhonet needs the XDenseUNet denoiser (SURVEY.md section 8f #1); '
-                                  'the Tikhonov step itself is models.Tikhonet.Tikhonov')
+        from models.XDenseUNet import XDenseUNet
+        from gdeconv.engine import XDenseEngine
+        self.tikhonov = Tikhonov(filter=filter)
+        self.denoiser = XDenseUNet()
+        self.lam = torch.tensor(1., requires_grad=True)
+        self._engine = [XDenseEngine(self, prefix='denoiser.')]
+
+    def forward(self, y, psf, alpha):
+        kind = _lib.SOLVER_TIKHONOV_ID if self.tikhonov.filter == 'Identity' else _lib.SOLVER_TIKHONOV_LAP
+        return self._engine[0].tikhonet(kind, float(self.lam.detach()), y, psf, alpha)

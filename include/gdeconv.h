@@ -112,6 +112,19 @@ GD_API int gd_conv_fft(const float* x, const float* psf, float* out, int adjoint
  * e12 [batch][2]. */
 GD_API int gd_moments_e(const float* img, float* e12, int batch, void* stream);
 
+/* XDenseUNet denoiser and the full Tikhonet / ShapeNet model (models/XDenseUNet.py:5-115, models/Tikhonet.py:34-47;
+ * SURVEY.md section 8f #1).  `tensors` is a state_dict as for gd_pack_weights; `prefix` is prepended to the XDenseUNet key
+ * names ("denoiser." for a Tikhonet state_dict, "" for a bare XDenseUNet).  The workspace needs no initialisation.
+ * gd_tikhonet_forward = clamp(y) -> Tikhonov(filter, lam) -> XDenseUNet -> * alpha. */
+typedef struct GdXDense GdXDense;
+GD_API int gd_pack_xdense(const GdTensorDesc* tensors, int n_tensors, const char* prefix, int device, GdXDense** out);
+GD_API void gd_free_xdense(GdXDense* x);
+GD_API size_t gd_xdense_workspace_bytes(int chunk);
+GD_API int gd_xdense_forward(const GdXDense* x, const float* in, float* out, int batch, void* workspace, size_t workspace_bytes,
+                             int chunk, void* stream);
+GD_API int gd_tikhonet_forward(const GdXDense* x, int filter, float lam, const float* y, const float* psf, const float* alpha,
+                               float* out, int batch, void* workspace, size_t workspace_bytes, int chunk, void* stream);
+
 /* Test hook: one tap-GEMM layer of the denoiser on caller-packed operands (layouts of csrc/gd_common.cuh:
  * activations [Kt/CH][Ptot][CH], CH = 8 halves (fp16 modes) or 4 floats; weights as gd_pack_weights lays them out
  * for `precision`; out32 [N/4][Ptot][4] fp32).  ntaps = 9 (3x3, zero padding) or 1.  `geom7` receives

@@ -365,6 +365,98 @@ class Tikhonov(nn.Module):
 
 
 # --------------------------------------------------------------------------
+# XDenseUNet + Tikhonet  (models/XDenseUNet.py:5-115, models/Tikhonet.py:34-47) -- SURVEY.md section 8f #1
+# --------------------------------------------------------------------------
+
+
+class _SepConv(nn.Module):
+    """models/XDenseUNet.py:5-18 (attribute name 'depthewise' is the reference's spelling = state_dict key)."""
+
+    def __init__(self, c, growth=12):
+        super().__init__()
+        self.depthewise = nn.Conv2d(c, c, 3, 1, 'same', 1, groups=c, bias=False)
+        self.pointwise = nn.Conv2d(c, growth, 1, 1, 0, 1, groups=1, bias=False)
+
+    def forward(self, x):
+        return self.pointwise(self.depthewise(x))
+
+
+class _DenseBlock(nn.Module):
+    """models/XDenseUNet.py:21-45: y <- cat(layer(y), y) per layer; optional cat(x, y) at the end."""
+
+    def __init__(self, n_layers, c_in, skip):
+        super().__init__()
+        self.skip_connection = skip
+        self.net = nn.Sequential(*[nn.Sequential(nn.BatchNorm2d(c_in + 12 * i), nn.ReLU(inplace=True), _SepConv(c_in + 12 * i))
+                                   for i in range(n_layers)])
+
+    def forward(self, x):
+        y = x
+        for layer in self.net:
+            y = torch.cat((layer(y), y), dim=1)
+        return torch.cat((x, y), dim=1) if self.skip_connection else y
+
+
+class _XDown(nn.Module):
+    """models/XDenseUNet.py:48-59."""
+
+    def __init__(self, ci, co):
+        super().__init__()
+        self.net = nn.Sequential(nn.BatchNorm2d(ci), nn.ReLU(inplace=True), nn.Conv2d(ci, co, 1, bias=False), nn.MaxPool2d(2, 2))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class _XUp(nn.Module):
+    """models/XDenseUNet.py:62-71."""
+
+    def __init__(self, ci, co):
+        super().__init__()
+        self.net = nn.Sequential(nn.Conv2d(ci, co, 1, bias=True), nn.Upsample(scale_factor=(2, 2), mode='nearest'))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class XDenseUNet(nn.Module):
+    """models/XDenseUNet.py:74-112."""
+
+    def __init__(self):
+        super().__init__()
+        self.input = nn.Sequential(nn.Conv2d(1, 32, 3, padding='same', bias=False), _DenseBlock(4, 32, True))
+        self.down1 = nn.Sequential(_XDown(112, 80), _DenseBlock(5, 80, True))
+        self.down2 = nn.Sequential(_XDown(220, 140), _DenseBlock(6, 140, True))
+        self.body = nn.Sequential(_XDown(352, 212), _DenseBlock(7, 212, False), _XUp(296, 84))
+        self.up1 = nn.Sequential(_DenseBlock(6, 436, False), _XUp(508, 72))
+        self.up2 = nn.Sequential(_DenseBlock(5, 292, False), _XUp(352, 60))
+        self.output = nn.Sequential(_DenseBlock(4, 172, False), nn.Conv2d(220, 1, 1, padding=0, bias=True))
+
+    def forward(self, x):
+        x1 = self.input(x)
+        x2 = self.down1(x1)
+        x3 = self.down2(x2)
+        x4 = self.body(x3)
+        x5 = self.up1(torch.cat((x3, x4), dim=1))
+        x6 = self.up2(torch.cat((x2, x5), dim=1))
+        return self.output(torch.cat((x1, x6), dim=1))
+
+
+class Tikhonet(nn.Module):
+    """models/Tikhonet.py:34-47: clamp -> Tikhonov(lam = 1, not a parameter) -> XDenseUNet -> * alpha."""
+
+    def __init__(self, filter='Identity'):
+        super().__init__()
+        self.tikhonov = Tikhonov(filter=filter)
+        self.denoiser = XDenseUNet()
+        self.lam = torch.tensor(1.)
+
+    def forward(self, y, psf, alpha):
+        y = torch.max(y, torch.zeros_like(y))
+        return self.denoiser(self.tikhonov(y, psf, alpha, self.lam)) * alpha
+
+
+# --------------------------------------------------------------------------
 # Moment ellipticities (measurement metric)
 # --------------------------------------------------------------------------
 

@@ -44,7 +44,7 @@ def main():
     from models.Unrolled_ADMM import Unrolled_ADMM
     from models.Richard_Lucy import Richard_Lucy
     from models.Wiener import Wiener
-    from models.Tikhonet import Tikhonov
+    from models.Tikhonet import Tikhonov, Tikhonet
     dev = torch.device('cuda:0')
     out = lambda **kw: print(json.dumps(kw), flush=True)
 
@@ -97,6 +97,10 @@ def main():
         obs[s:s + piece], psf[s:s + piece], alpha[s:s + piece] = bb['obs'], bb['psf'], bb['alpha']
     del bb
     hbm = 6554.6
+    tk = Tikhonet('Laplacian').eval().to(dev)                # seeded weights: throughput only (trained-weight parity: tests/test_tikhonet.py)
+    nt = min(N, 100000)
+    ms = timed(lambda: tk(obs[:nt], psf[:nt], alpha[:nt]), steps=2, warmup=1)
+    out(config=4, model='Tikhonet_Laplacian (Tikhonov + XDenseUNet, fp32 CUDA cores)', stamps=nt, ms_per_step=ms, galaxies_per_s=nt / ms * 1e3)
     for name, fn, nbytes in (('Wiener', lambda: Wiener()(obs, psf, alpha), 27652), ('Tikhonov_Laplacian', lambda: Tikhonov('Laplacian')(obs, psf, alpha, 1.0), 27652),
                              ('Richard_Lucy(10)', lambda: Richard_Lucy(10)(obs, psf), 27648), ('Richard_Lucy(50)', lambda: Richard_Lucy(50)(obs, psf), 27648),
                              ('Richard_Lucy(100)', lambda: Richard_Lucy(100)(obs, psf), 27648)):
