@@ -54,6 +54,7 @@ struct GdWeights {
     size_t blob_bytes;
     const float* head;                // [9][C0] fp32
     const float* tail;                // [9][C0] fp32
+    float head_h[9 * 64], tail_h[9 * 64];   // host copies (C0 <= 64): kernel-parameter weights of the head/tail-fused epilogue
     const void* down_rb[3][2][2];     // down stage L, ResBlock, conv  (3x3, C_L -> C_L)
     const void* down[3];              // k2s2 strided conv C_L -> C_{L+1}
     const void* body_rb[2][2];
@@ -144,7 +145,12 @@ static int pack_up(Blob& bl, const GdTensorDesc* t, int Ci, int Co, int prec, si
     std::vector<float> B((size_t)Ci * 4 * Co);
     for (int ci = 0; ci < Ci; ++ci)
         for (int co = 0; co < Co; ++co)
-            for (int tp = 0; tp < 4; ++tp) B[(size_t)ci * 4 * Co + tp * Co + co] = t->data[((size_t)ci * Co + co) * 4 + tp];
+            for (int tp = 0; tp < 4; ++tp) {
+                // tcgen05 path: columns ordered for the lane-paired stores of epi_up_unit (conv_epilogue.cuh)
+                const int dy = tp >> 1, dx = tp & 1;
+                const int n = prec == PREC_FP16_UMMA ? dy * 2 * Co + (co / 16) * 32 + ((co % 16) / 4) * 8 + dx * 4 + (co % 4) : tp * Co + co;
+                B[(size_t)ci * 4 * Co + n] = t->data[((size_t)ci * Co + co) * 4 + tp];
+            }
     *off = pack_tapgemm(bl, 1, Ci, 4 * Co, prec, B);
     return GD_OK;
 }
@@ -210,6 +216,7 @@ extern "C" int gd_pack_weights(int arch, int n_iters, const GdTensorDesc* tensor
             if (!shape_is(tt, 1, C0, 3, 3)) GD_FAIL(GD_EBADSHAPE, "m_tail.weight: missing or not (1,%d,3,3)", C0);
             for (int c = 0; c < C0; ++c)
                 for (int tp = 0; tp < 9; ++tp) { h[(size_t)tp * C0 + c] = th->data[(size_t)c * 9 + tp]; tl[(size_t)tp * C0 + c] = tt->data[(size_t)c * 9 + tp]; }
+            if (C0 <= 64) { memcpy(W.head_h, h.data(), h.size() * sizeof(float)); memcpy(W.tail_h, tl.data(), tl.size() * sizeof(float)); }
             slot((const void**)&W.head, pack_f32(bl, h.data(), h.size()));
             slot((const void**)&W.tail, pack_f32(bl, tl.data(), tl.size()));
         }
@@ -338,6 +345,7 @@ struct Ws {
     float *skip32[4], *p32a[4], *p32b[4];
     void *a16[4], *t16[4], *d16[4];
     unsigned int* chain_flags;                 // per-(layer, item) completion counters of the layer-chained kernel
+    float *tpad, *tail_part;                   // head/tail fusion (conv_umma.cu EPI_HT): padded-linear input, per-tap tail sums
 };
 
 static Ws ws_layout(unsigned char* base, int arch, int prec, int chunk) {
@@ -371,6 +379,8 @@ static Ws ws_layout(unsigned char* base, int arch, int prec, int chunk) {
         if (L > 0) w.d16[L] = take((size_t)2 * n * es);        // 4*C_{L-1} = 2*C_L channels
     }
     w.chain_flags = (unsigned int*)take(chain_flag_words(w.g[0].Ptot) * sizeof(unsigned int));
+    w.tpad = (float*)take((size_t)w.g[0].Ptot * 4);
+    w.tail_part = (float*)take((size_t)(C0 / 32) * 9 * w.g[0].Ptot * 4);
     w.total = off;
     return w;
 }
@@ -432,6 +442,15 @@ static int chain_mode() {
     }
     return g_chain;
 }
+// Head/tail fusion of the tcgen05 path (GDECONV_FUSE_HT=0 restores the stored fp32 head output and the k_tail kernel).
+static int g_fuse_ht = -1;
+static int fuse_ht_mode() {
+    if (g_fuse_ht < 0) {
+        const char* e = getenv("GDECONV_FUSE_HT");
+        g_fuse_ht = e ? atoi(e) : 1;
+    }
+    return g_fuse_ht;
+}
 static int g_subchunk = 0;
 static int subchunk_size() {
     if (!g_subchunk) {
@@ -450,11 +469,14 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
     auto at = [&](const void* base, int L, int s0) -> unsigned char* {
         return base ? (unsigned char*)base + (size_t)s0 * g[L].S * 16 : nullptr;
     };
+    // tcgen05 path: x1 is never stored in fp32; its consumers recompute it from tpad (ConvParams::head_t)
+    const bool fuse = prec == PREC_FP16_UMMA && !chain_mode() && fuse_ht_mode() && C[0] <= 64;
     {   // head (ResUNet.py:31): x1 = conv(t)  -> skip32[0] (fp32) + a16[0]
         ConvParams p = conv_base(g[0], nb);
-        p.N = C[0]; p.out32 = ws.skip32[0]; p.out16 = ws.a16[0];
-        GD_TRY(launch_head(t, W->head, C[0], p, nb, prec, st));
+        p.N = C[0]; p.out32 = fuse ? nullptr : ws.skip32[0]; p.out16 = ws.a16[0];
+        GD_TRY(launch_head(t, W->head, C[0], p, nb, prec, fuse ? ws.tpad : nullptr, st));
     }
+    auto at4 = [&](float* base, int s0) -> float* { return base + (size_t)s0 * g[0].S; };    // 4-byte rows of level 0
     // one ResBlock (resnet_basicblock.py:69-71) on stamps [s0, s0+n): stream + conv(relu(conv(stream))) -> two layers
     auto rb_params = [&](int L, int s0, int n, const void* const* w2, const float* res, const float* skip, float* out32,
                          void* out16, void* s2d, ConvParams* out) {
@@ -465,10 +487,18 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         out[1].out32 = (float*)at(out32, L, s0); out[1].out16 = at(out16, L, s0);
         if (s2d) { out[1].s2d = at(s2d, L + 1, s0); out[1].gc = g[L + 1]; out[1].gc.M = n * g[L + 1].S; }
     };
+    // head/tail fusion hooks for the second conv of the next resblock() call (level 0, consumed once)
+    bool ht_res_is_head = false, ht_skip_is_head = false, ht_tail = false;
     auto resblock = [&](int L, int s0, int n, const void* const* w2, const float* res, const float* skip, float* out32,
                         void* out16, void* s2d) -> int {
         ConvParams p[2];
         rb_params(L, s0, n, w2, res, skip, out32, out16, s2d, p);
+        if (ht_res_is_head || ht_skip_is_head) {
+            p[1].head_t = at4(ws.tpad, s0); p[1].head_w = W->head_h;
+            if (ht_res_is_head) p[1].res32 = nullptr; else p[1].skip32 = nullptr;
+        }
+        if (ht_tail) { p[1].tail_part = at4(ws.tail_part, s0); p[1].tail_w = W->tail_h; p[1].out32 = nullptr; p[1].out16 = nullptr; }
+        ht_res_is_head = ht_skip_is_head = ht_tail = false;
         if (prec == PREC_FP16_UMMA && chain_mode() && C[L] == 64) return launch_conv_chain(p, 2, ws.chain_flags, st);
         GD_TRY(run_conv(p[0], prec, st));
         return run_conv(p[1], prec, st);
@@ -482,7 +512,10 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
             rb_params(L, s0, n, wb, res_b, skip_b, out32_b, out16_b, s2d_b, p + 2);
             return launch_conv_chain(p, 4, ws.chain_flags, st);
         }
+        const bool last_l0 = fuse && L == 0 && skip_b != nullptr;       // second ResBlock of m_up1: + x1, then m_tail
+        if (fuse && L == 0 && res_a == ws.skip32[0]) ht_res_is_head = true;   // first ResBlock of m_down1: residual = x1
         GD_TRY(resblock(L, s0, n, wa, res_a, nullptr, out32_a, out16_a, nullptr));
+        if (last_l0) { ht_skip_is_head = true; ht_tail = true; }
         return resblock(L, s0, n, wb, res_b, skip_b, out32_b, out16_b, s2d_b);
     };
     auto down_stage = [&](int L, int s0, int n) -> int {          // m_down{L+1} (ResUNet.py:32-34)
@@ -521,6 +554,7 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         GD_TRY(up_stage(0, s0, n));
     }
     // tail (ResUNet.py:39): conv(x + x1), times the per-stamp input scale
+    if (fuse) return launch_tail_gather(ws.tail_part, C[0] / 32, g[0], tscale, zout, nb, st);
     return launch_tail(ws.p32a[0], W->tail, C[0], g[0], tscale, zout, nb, st);
 }
 

@@ -204,4 +204,52 @@ __device__ __forceinline__ void epi_out16(const ConvParams& p, const RowCtx& rc,
     }
 }
 
+// ---- k2s2 transposed conv (mode 1) on the tcgen05 path: sector-complete pixel-shuffle stores ----
+// Column order of the packed weights (api.cu pack_up, PREC_FP16_UMMA):
+//     n = dy*(2*Cf) + (c/16)*32 + ((c%16)/4)*8 + dx*4 + (c%4)
+// so one 32-column accumulator unit holds 16 channels [c0, c0+16) of BOTH sub-pixels dx = 0,1 of fine row 2Y+dy.
+// A lane owns one coarse pixel, i.e. the fine pixels o = 2*lane + dx of the warp's run of 64; stored directly, every warp
+// store would put 16 bytes at a 32-byte stride (half-filled sectors: measured ~2 TB/s and DRAM read-modify-write fills).
+// The unit is therefore transposed through a warp-private 4 KB shared-memory stage (16-byte pieces XOR-swizzled, both
+// directions conflict-free): afterwards lane l of store j holds fine pixel 32*j + l, and a warp store covers 512
+// contiguous bytes.  Rows and validity travel with the data (shuffles), so coarse-row wrap-arounds inside the warp are
+// handled exactly.  Must be called by all 32 lanes.
+__device__ __forceinline__ void epi_up_unit(const ConvParams& p, bool valid, int frow0, int n0, const float* v, float4* stage) {
+    const int lane = threadIdx.x & 31;
+    const int dy = n0 >> (p.Cf_log2 + 1), c0 = ((n0 & (2 * p.Cf - 1)) >> 5) * 16;
+    const int R0 = frow0 + dy * p.gf.Wp;
+#pragma unroll
+    for (int pc = 0; pc < 8; ++pc) {             // piece pc = dx*4 + g: channels 4g..4g+3 of sub-pixel dx
+        const int g = pc & 3, dx = pc >> 2;
+        stage[8 * lane + (pc ^ (lane & 7))] = make_float4(v[g * 8 + dx * 4], v[g * 8 + dx * 4 + 1], v[g * 8 + dx * 4 + 2], v[g * 8 + dx * 4 + 3]);
+    }
+    __syncwarp();
+    const size_t Pf = (size_t)p.gf.Ptot;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int src = 16 * j + (lane >> 1), dx = lane & 1;
+        const int row = __shfl_sync(0xffffffffu, R0, src) + dx;
+        const bool ok = __shfl_sync(0xffffffffu, (int)valid, src) != 0;
+        float4 x[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) x[g] = stage[8 * src + ((dx * 4 + g) ^ (src & 7))];
+        if (ok) {
+            if (p.out32) {
+                float4* o = reinterpret_cast<float4*>(p.out32) + (size_t)(c0 >> 2) * Pf + row;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) o[(size_t)g * Pf] = x[g];
+            }
+            if (p.out16) {
+                uint4* o = reinterpret_cast<uint4*>(p.out16) + (size_t)(c0 >> 3) * Pf + row;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float a[8] = {x[2 * h].x, x[2 * h].y, x[2 * h].z, x[2 * h].w, x[2 * h + 1].x, x[2 * h + 1].y, x[2 * h + 1].z, x[2 * h + 1].w};
+                    o[(size_t)h * Pf] = pack8_half(a);
+                }
+            }
+        }
+    }
+    __syncwarp();                                // the stage is reused by the warp's next unit
+}
+
 }  // namespace gd

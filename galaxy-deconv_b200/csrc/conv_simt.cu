@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(128) k_conv_simt(const ConvParams p) {
 // weights w[tap][C0] fp32.
 template <typename T>
 __global__ void __launch_bounds__(128) k_head(const float* __restrict__ t, const float* __restrict__ w, int C0,
-                                              ConvParams p, int batch) {
-    extern __shared__ float wsm[];           // 9*C0
+                                              ConvParams p, int batch, float* __restrict__ tpad) {
+    extern __shared__ __align__(16) float wsm[];           // 9*C0
     for (int i = threadIdx.x; i < 9 * C0; i += blockDim.x) wsm[i] = w[i];
     __syncthreads();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,14 +89,20 @@ __global__ void __launch_bounds__(128) k_head(const float* __restrict__ t, const
         }
     RowCtx rc;
     rc.valid = true; rc.row = p.g.base0 + b * p.g.S + y * p.g.Wp + x; rc.crow = 0; rc.ctap = 0; rc.frow0 = 0;
+    if (tpad) tpad[rc.row] = in[4];          // padded-linear copy of the input for the head-recomputing epilogues (EPI_HT)
     for (int n0 = 0; n0 < C0; n0 += 16) {
         float acc[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            float s = 0.f;
+        for (int c = 0; c < 16; ++c) acc[c] = 0.f;
 #pragma unroll
-            for (int tp = 0; tp < 9; ++tp) s = fmaf(in[tp], wsm[tp * C0 + n0 + c], s);
-            acc[c] = s;
+        for (int tp = 0; tp < 9; ++tp) {         // per channel: fma chain over the taps in order 0..8 (LDS.128 weight loads)
+            const float4* w4 = reinterpret_cast<const float4*>(wsm + tp * C0 + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 ww = w4[q];
+                acc[4 * q] = fmaf(in[tp], ww.x, acc[4 * q]); acc[4 * q + 1] = fmaf(in[tp], ww.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(in[tp], ww.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(in[tp], ww.w, acc[4 * q + 3]);
+            }
         }
         epilogue_store16<T>(p, rc, n0, acc);
     }
@@ -140,6 +146,23 @@ __global__ void __launch_bounds__(TAIL_ROWS) k_tail(const float* __restrict__ x3
     z[(size_t)b * NPIX + y * STAMP + x] = s * tscale[b];
 }
 
+// Tail of the head/tail-fused tcgen05 path: the last conv of m_up1 left P[u*9 + tap][row] = sum_c w_tail[tap][c] * (x + x1)[row][c]
+// (32-channel unit u); m_tail (ResUNet.py:39) is then z[m] = sum_tap sum_u P[u*9 + tap][m + off(tap)], times the per-stamp
+// power-of-two input scale.  Halo rows of P are never written (zero since gd_workspace_init).
+__global__ void __launch_bounds__(256) k_tail_gather(const float* __restrict__ P, int units, Geom g, const float* __restrict__ tscale,
+                                                     float* __restrict__ z, int batch) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * NPIX) return;
+    const int b = idx / NPIX, r = idx - b * NPIX, y = r / STAMP, x = r - y * STAMP;
+    const float* src = P + (g.base0 + b * g.S + y * g.Wp + x);
+    float s = 0.f;
+    for (int u = 0; u < units; ++u) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) s += __ldg(src + (size_t)(u * 9 + t) * g.Ptot + (t / 3 - 1) * g.Wp + (t % 3 - 1));
+    }
+    z[idx] = s * tscale[b];
+}
+
 // ---- host launchers ----
 int launch_conv_simt(const ConvParams& p, int prec, cudaStream_t st) {
     if (p.g.M <= 0) return GD_OK;
@@ -150,11 +173,18 @@ int launch_conv_simt(const ConvParams& p, int prec, cudaStream_t st) {
     return GD_OK;
 }
 
-int launch_head(const float* t, const float* w, int C0, const ConvParams& p, int batch, int prec, cudaStream_t st) {
+int launch_head(const float* t, const float* w, int C0, const ConvParams& p, int batch, int prec, float* tpad, cudaStream_t st) {
     int n = batch * NPIX, blocks = (n + 127) / 128;
     if (n <= 0) return GD_OK;
-    if (prec == PREC_FP32_SIMT) k_head<float><<<blocks, 128, 9 * C0 * sizeof(float), st>>>(t, w, C0, p, batch);
-    else k_head<__half><<<blocks, 128, 9 * C0 * sizeof(float), st>>>(t, w, C0, p, batch);
+    if (prec == PREC_FP32_SIMT) k_head<float><<<blocks, 128, 9 * C0 * sizeof(float), st>>>(t, w, C0, p, batch, tpad);
+    else k_head<__half><<<blocks, 128, 9 * C0 * sizeof(float), st>>>(t, w, C0, p, batch, tpad);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+
+int launch_tail_gather(const float* P, int units, const Geom& g, const float* tscale, float* z, int batch, cudaStream_t st) {
+    if (batch <= 0) return GD_OK;
+    k_tail_gather<<<(batch * NPIX + 255) / 256, 256, 0, st>>>(P, units, g, tscale, z, batch);
     GD_LAUNCHED();
     return GD_OK;
 }

@@ -43,11 +43,39 @@ struct UmmaCfg {
     int nsl_log2, nb32_log2;   // log2(nslices), log2(ncta / 32): both are powers of two
     int abl;         // diagnostic ablation bits (GDECONV_ABL): 1 = no weight streaming, 2 = no epilogue global traffic, 4 = no activation loads
     int l2pf;        // producer prefetches the residual / skip rows of each item into L2
+    int aux_off;     // mode 1: byte offset of the 8 warp-private 4 KB transpose stages of epi_up_unit in dynamic shared memory
     size_t smem;
 };
 
+// EPI_HT: the fp32 m_head / m_tail weights travel as kernel parameters, so that every weight is an immediate
+// constant-bank operand of its FFMA (no shared-memory loads on the epilogue's critical path: with two epilogue warps per
+// scheduler their latency was fully exposed).  N = 128 / J for the two level-0 shapes (G: N = 32, J = 4; U: N = 64, J = 2).
+template <int EPI, int N>
+struct HtWeights { float head[EPI == EPI_HT ? 9 * N : 1], tail[EPI == EPI_HT ? 9 * N : 1]; };
+
+// v[0..31] += m_head(t)[N0 .. N0+31]: 9 taps x 32 channels, weights straight from the constant bank
+template <int N, int N0>
+__device__ __forceinline__ void ht_head(const float* __restrict__ hw, const float* hcur, float* v) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = fmaf(hcur[t], hw[t * N + N0 + k], v[k]);
+}
+// 9 per-tap partial sums of m_tail over channels N0 .. N0+31 (four independent chains per tap)
+template <int N, int N0>
+__device__ __forceinline__ void ht_tail(const float* __restrict__ tw, const float* v, float* dst, size_t Ptot) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s[k & 3] = fmaf(v[k], tw[t * N + N0 + k], s[k & 3]);
+        dst[(size_t)t * Ptot] = (s[0] + s[1]) + (s[2] + s[3]);
+    }
+}
+
 template <int J, int KK, int EPI>
-__global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams p, const UmmaCfg c) {
+__global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams p, const UmmaCfg c,
+                                                               const __grid_constant__ HtWeights<EPI, 128 / J> htw) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 5];
     __shared__ uint32_t tmem_slot;
@@ -207,11 +235,11 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
             const Geom& g = p.g;
             const uint32_t Ptot = (uint32_t)g.Ptot;
             constexpr int UPW_PREF = 2;                      // units per warp whose residual is prefetched one item ahead
-            float add[EPI == EPI_FULL ? UPW_PREF : 1][32];
+            float add[EPI != EPI_PLAIN ? UPW_PREF : 1][32];
             // row decomposition of GEMM row m: validity + absolute row (+ s2d / pixel-shuffle targets via make_row_ctx)
             auto unit_of = [&](int i) { return nu == 1 ? 0 : half + 2 * i; };
             auto issue_res = [&](int item, int i) {
-                if (EPI != EPI_FULL || !p.res32 || p.mode == 1 || i >= UPW_PREF || (c.abl & 2)) return;
+                if (EPI == EPI_PLAIN || !p.res32 || p.mode == 1 || i >= UPW_PREF || (c.abl & 2)) return;
                 const int im = item >> c.nsl_log2, ns = item & (c.nslices - 1);
                 const int uu = unit_of(i), j = uu >> c.nb32_log2, b = uu & (nb32 - 1);
                 const int m = (im * J + j) * MTILE + q * 32 + lane;
@@ -220,7 +248,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     float4 t = __ldg(src + (size_t)k * Ptot);
-                    float* d = add[EPI == EPI_FULL && i < UPW_PREF ? i : 0];
+                    float* d = add[EPI != EPI_PLAIN && i < UPW_PREF ? i : 0];
                     d[4 * k] = t.x; d[4 * k + 1] = t.y; d[4 * k + 2] = t.z; d[4 * k + 3] = t.w;
                 }
             };
@@ -267,6 +295,14 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                     } else {
                         RowCtx rc = make_row_ctx(p, m);
                         if (c.abl & 2) rc.valid = false;
+                        float hcur[9];
+                        if constexpr (EPI == EPI_HT) {
+                            if (p.head_t && m < g.M) {           // 3x3 neighbourhood of the 1-channel denoiser input
+                                const float* tp = p.head_t + (g.base0 + m);
+#pragma unroll
+                                for (int t = 0; t < 9; ++t) hcur[t] = __ldg(tp + p.off[t]);
+                            }
+                        }
                         tc_ld_wait16(r0);
                         tc_ld_wait16(r1);
 #pragma unroll
@@ -278,7 +314,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                         if (p.res32 && p.mode == 0 && m < g.M && !(c.abl & 2)) {
                             if (i < UPW_PREF) {
 #pragma unroll
-                                for (int k = 0; k < 32; ++k) v[k] += add[EPI == EPI_FULL && i < UPW_PREF ? i : 0][k];
+                                for (int k = 0; k < 32; ++k) v[k] += add[EPI != EPI_PLAIN && i < UPW_PREF ? i : 0][k];
                             } else {                        // units beyond the prefetch depth (streamed-weight layers): load at use
                                 const float4* src = reinterpret_cast<const float4*>(p.res32) + (size_t)(n0 >> 2) * Ptot + (g.base0 + m);
 #pragma unroll
@@ -289,6 +325,27 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                             }
                         }
                         if (nitem < total_items) issue_res(nitem, i);          // registers of unit i are free again
+                        if constexpr (EPI == EPI_FULL) {
+                            if (p.mode == 1) {                   // transposed conv: lane-paired pixel-shuffle stores
+                                epi_up_unit(p, rc.valid, rc.frow0, n0, v, reinterpret_cast<float4*>(smem + c.aux_off) + e * 256);
+                                continue;
+                            }
+                        }
+                        if constexpr (EPI == EPI_HT) {
+                            constexpr int HN = 128 / J;
+                            if (p.head_t) {                      // + m_head(t)[n0 .. n0+31] (rows that are not stored may hold anything)
+                                if (HN == 32 || n0 == 0) ht_head<HN, 0>(htw.head, hcur, v);
+                                else ht_head<HN, HN == 32 ? 0 : 32>(htw.head, hcur, v);
+                            }
+                            if (p.tail_part) {                   // 9 per-tap partial sums of m_tail instead of the 32 channels
+                                if (rc.valid) {
+                                    float* dst = p.tail_part + (size_t)((n0 >> 5) * 9) * Ptot + rc.row;
+                                    if (HN == 32 || n0 == 0) ht_tail<HN, 0>(htw.tail, v, dst, Ptot);
+                                    else ht_tail<HN, HN == 32 ? 0 : 32>(htw.tail, v, dst, Ptot);
+                                }
+                                continue;
+                            }
+                        }
                         if (rc.valid) {
                             const EpiAddr a0 = epi_addr(p, rc, n0), a1 = epi_addr(p, rc, n0 + 16);
                             if (p.skip32) {
@@ -364,6 +421,8 @@ int conv_umma_init() {
     GD_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma<J, KK, EPI_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX))
     GD_UMMA_ATTR(1, 2); GD_UMMA_ATTR(2, 2); GD_UMMA_ATTR(4, 2); GD_UMMA_ATTR(1, 4); GD_UMMA_ATTR(2, 4); GD_UMMA_ATTR(4, 4);
 #undef GD_UMMA_ATTR
+    GD_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma<2, 2, EPI_HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX));
+    GD_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma<4, 2, EPI_HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX));
     return GD_OK;
 }
 
@@ -381,7 +440,15 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     c.b_resident = (size_t)c.b_total_bytes <= B_RESIDENT_MAX;
     c.b_stage_bytes = c.ncta * c.BK * 2;
     c.b_stages = c.b_resident ? 0 : g_bstages;
-    const size_t b_region = c.b_resident ? (size_t)c.b_total_bytes : (size_t)c.b_stages * c.b_stage_bytes;
+    size_t b_region = c.b_resident ? (size_t)c.b_total_bytes : (size_t)c.b_stages * c.b_stage_bytes;
+    if (p.head_t || p.tail_part) {                // EPI_HT (weights are kernel parameters)
+        if (p.mode != 0 || p.ntaps != 9 || (p.N != 32 && p.N != 64) || p.skip32 || p.s2d || (p.head_t && !p.head_w) || (p.tail_part && !p.tail_w)) {
+            set_error("conv_umma: head/tail fusion needs a 3x3 level-0 layer with N = 32 or 64"); return GD_EUNSUPPORTED;
+        }
+    } else if (p.mode == 1) {
+        c.aux_off = (int)((b_region + 127) / 128 * 128);
+        b_region = (size_t)c.aux_off + (size_t)EPI_WARPS * 4096;
+    }
     // resident weights: <= 128 accumulator columns per item (2 epilogue units per warp, fine-grained A ring, good tail
     // balance); streamed weights: 256 columns so that every weight stage is reused by twice as many rows
     c.J = (c.b_resident ? 128 : ACC_STAGE_COLS) / c.ncta;
@@ -395,6 +462,7 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     if (c.a_stages > MAX_A_STAGES) c.a_stages = MAX_A_STAGES;
     if (c.a_stages < 2) { set_error("conv_umma: layer does not fit shared memory"); return GD_EUNSUPPORTED; }
     c.smem = (size_t)c.a_stages * c.a_stage_bytes + b_region;
+    if (p.mode == 1) c.aux_off += c.a_stages * c.a_stage_bytes;     // relative to the start of dynamic smem
     const int tiles = (p.g.M + MTILE - 1) / MTILE;
     c.items_m = (tiles + c.J - 1) / c.J;
     c.l2pf = g_l2pf;
@@ -423,15 +491,26 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t st) {
         GD_CUDA_CHECK(cudaEventRecord(e0, st));
     }
     const int KK = c.BK / 16;
-    const bool plain = p.mode == 0 && !p.res32 && !p.skip32 && !p.out32 && !p.s2d && p.out16;
+    const bool ht = p.head_t || p.tail_part;
+    const bool plain = p.mode == 0 && !p.res32 && !p.skip32 && !p.out32 && !p.s2d && p.out16 && !ht;
 #define GD_UMMA_GO(JJ, KKK)                                                                         \
-    if (c.J == JJ && KK == KKK) {                                                                   \
-        if (plain) k_conv_umma<JJ, KKK, EPI_PLAIN><<<grid, UMMA_THREADS, c.smem, st>>>(p, c);       \
-        else k_conv_umma<JJ, KKK, EPI_FULL><<<grid, UMMA_THREADS, c.smem, st>>>(p, c);              \
+    if (c.J == JJ && KK == KKK && !ht) {                                                            \
+        if (plain) k_conv_umma<JJ, KKK, EPI_PLAIN><<<grid, UMMA_THREADS, c.smem, st>>>(p, c, HtWeights<EPI_PLAIN, 128 / JJ>()); \
+        else k_conv_umma<JJ, KKK, EPI_FULL><<<grid, UMMA_THREADS, c.smem, st>>>(p, c, HtWeights<EPI_FULL, 128 / JJ>());         \
     } else
+#define GD_UMMA_GO_HT(JJ, KKK)                                                                      \
+    if (c.J == JJ && KK == KKK && ht && p.N == 128 / JJ) {                                          \
+        HtWeights<EPI_HT, 128 / JJ> hw;                                                             \
+        memset(&hw, 0, sizeof(hw));                                                                 \
+        if (p.head_t) memcpy(hw.head, p.head_w, sizeof(hw.head));                                   \
+        if (p.tail_part) memcpy(hw.tail, p.tail_w, sizeof(hw.tail));                                \
+        k_conv_umma<JJ, KKK, EPI_HT><<<grid, UMMA_THREADS, c.smem, st>>>(p, c, hw);                 \
+    } else
+    GD_UMMA_GO_HT(2, 2) GD_UMMA_GO_HT(4, 2)
     GD_UMMA_GO(1, 2) GD_UMMA_GO(2, 2) GD_UMMA_GO(4, 2) GD_UMMA_GO(1, 4) GD_UMMA_GO(2, 4) GD_UMMA_GO(4, 4)
     { set_error("conv_umma: no kernel variant for J=%d, BK=%d", c.J, c.BK); return GD_EUNSUPPORTED; }
 #undef GD_UMMA_GO
+#undef GD_UMMA_GO_HT
     GD_LAUNCHED();
     if (e1) GD_CUDA_CHECK(cudaEventRecord(e1, st));
     return GD_OK;

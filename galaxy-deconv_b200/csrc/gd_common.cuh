@@ -92,6 +92,15 @@ struct ConvParams {
     int Cf, Cf_log2;
     Geom gc;                  // coarse level (s2d target)
     Geom gf;                  // fine level (mode 1 target)
+    // head / tail fusion (tcgen05 path, level 0 only; conv_umma.cu EPI_HT).  The fp32 output of m_head (ResUNet.py:31)
+    // is never stored: wherever it is consumed as a residual or as the final U-Net skip (ResUNet.py:39) the epilogue
+    // recomputes it from the 1-channel padded-linear input `head_t` (9 FMAs per channel).  The last conv of m_up1 does
+    // not store its 32-channel result either: it reduces it against the m_tail weights into 9 per-tap partial sums per
+    // row, `tail_part[(n/32)*9 + tap][row]`, which k_tail_gather shifts and adds (4.5x fewer bytes than the stream).
+    const float* head_t;      // [g.Ptot] fp32, zero halos
+    const float* head_w;      // [9][N] fp32, HOST pointer: copied into the kernel parameters (constant bank) at launch
+    float* tail_part;         // [(N/32)*9][g.Ptot] fp32
+    const float* tail_w;      // [9][N] fp32, HOST pointer
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -9,7 +9,7 @@
 namespace gd {
 
 // ---- kernel shape constants shared by conv_umma.cu and conv_chain.cu ----
-enum { EPI_PLAIN = 0, EPI_FULL = 1 };
+enum { EPI_PLAIN = 0, EPI_FULL = 1, EPI_HT = 2 };   // EPI_HT = EPI_FULL + head recompute / tail partial sums (level 0)
 constexpr int EPI_WARPS = 8;
 constexpr int MMA_WARPS = 4;                        // warps 1..4: MMA issuers, one 128-row tile of the item each (J <= 4)
 constexpr int EPI_WARP0 = 1 + MMA_WARPS;            // warps 5..12: epilogue
