@@ -180,6 +180,7 @@ static int init_once(int device) {
     GD_TRY(subnet_init());
     GD_TRY(conv_umma_init());
     GD_TRY(conv_chain_init());
+    GD_TRY(conv_rb_init());
     done.fetch_or(1u << device);
     return GD_OK;
 }
@@ -380,7 +381,7 @@ static Ws ws_layout(unsigned char* base, int arch, int prec, int chunk) {
     }
     w.chain_flags = (unsigned int*)take(chain_flag_words(w.g[0].Ptot) * sizeof(unsigned int));
     w.tpad = (float*)take((size_t)w.g[0].Ptot * 4);
-    w.tail_part = (float*)take((size_t)(C0 / 32) * 9 * w.g[0].Ptot * 4);
+    w.tail_part = (float*)take((size_t)(C0 / 16) * 9 * w.g[0].Ptot * 4);   // 32-channel units (conv_umma.cu) or 16-channel halves (conv_rb.cu)
     w.total = off;
     return w;
 }
@@ -451,6 +452,15 @@ static int fuse_ht_mode() {
     }
     return g_fuse_ht;
 }
+// Fused ResBlock kernel at the 32-channel level (conv_rb.cu); GDECONV_FUSE_RB=0 restores one launch per conv.
+static int g_fuse_rb = -1;
+static int fuse_rb_mode() {
+    if (g_fuse_rb < 0) {
+        const char* e = getenv("GDECONV_FUSE_RB");
+        g_fuse_rb = e ? atoi(e) : 1;
+    }
+    return g_fuse_rb;
+}
 static int g_subchunk = 0;
 static int subchunk_size() {
     if (!g_subchunk) {
@@ -478,11 +488,16 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
     }
     auto at4 = [&](float* base, int s0) -> float* { return base + (size_t)s0 * g[0].S; };    // 4-byte rows of level 0
     // one ResBlock (resnet_basicblock.py:69-71) on stamps [s0, s0+n): stream + conv(relu(conv(stream))) -> two layers
+    // fp16 input of the next resblock() call; nullptr = ws.a16[L].  The fused ResBlock kernel (conv_rb.cu) must not write its
+    // fp16 output over its own input (neighbouring work items still read it as halo), so pairs ping-pong a16 <-> t16.
+    const void* rb_in16 = nullptr;
     auto rb_params = [&](int L, int s0, int n, const void* const* w2, const float* res, const float* skip, float* out32,
                          void* out16, void* s2d, ConvParams* out) {
-        out[0] = conv3(g[L], n, C[L], at(ws.a16[L], L, s0), w2[0], 1);
-        out[0].out16 = at(ws.t16[L], L, s0);
-        out[1] = conv3(g[L], n, C[L], at(ws.t16[L], L, s0), w2[1], 0);
+        const void* in16 = rb_in16 ? rb_in16 : ws.a16[L];
+        void* mid16 = in16 == ws.t16[L] ? ws.a16[L] : ws.t16[L];          // intermediate ReLU(conv1(x)) (unfused launches only)
+        out[0] = conv3(g[L], n, C[L], at(in16, L, s0), w2[0], 1);
+        out[0].out16 = at(mid16, L, s0);
+        out[1] = conv3(g[L], n, C[L], at(mid16, L, s0), w2[1], 0);
         out[1].res32 = (const float*)at(res, L, s0); out[1].skip32 = (const float*)at(skip, L, s0);
         out[1].out32 = (float*)at(out32, L, s0); out[1].out16 = at(out16, L, s0);
         if (s2d) { out[1].s2d = at(s2d, L + 1, s0); out[1].gc = g[L + 1]; out[1].gc.M = n * g[L + 1].S; }
@@ -499,7 +514,14 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         }
         if (ht_tail) { p[1].tail_part = at4(ws.tail_part, s0); p[1].tail_w = W->tail_h; p[1].out32 = nullptr; p[1].out16 = nullptr; }
         ht_res_is_head = ht_skip_is_head = ht_tail = false;
+        rb_in16 = nullptr;
         if (prec == PREC_FP16_UMMA && chain_mode() && C[L] == 64) return launch_conv_chain(p, 2, ws.chain_flags, st);
+        // fused kernel, except (mode 1) for the ResBlock that ends in the m_tail partial sums: its FMA-heavy epilogue is
+        // faster on the eight 32-channel epilogue warps of conv_umma.cu (profiles/README); GDECONV_FUSE_RB=2 fuses it too
+        if (prec == PREC_FP16_UMMA && !chain_mode() && fuse_rb_mode() && conv_rb_supported(p[0], p[1]) &&
+            (fuse_rb_mode() >= 2 || !p[1].tail_part))
+            return launch_conv_rb(p[0], p[1], st);
+        if (p[0].a == p[0].out16 || p[1].a == p[1].out16) GD_FAIL(GD_EUNSUPPORTED, "resblock: in-place fp16 buffers need the fused kernel");
         GD_TRY(run_conv(p[0], prec, st));
         return run_conv(p[1], prec, st);
     };
@@ -514,8 +536,10 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         }
         const bool last_l0 = fuse && L == 0 && skip_b != nullptr;       // second ResBlock of m_up1: + x1, then m_tail
         if (fuse && L == 0 && res_a == ws.skip32[0]) ht_res_is_head = true;   // first ResBlock of m_down1: residual = x1
-        GD_TRY(resblock(L, s0, n, wa, res_a, nullptr, out32_a, out16_a, nullptr));
+        const bool pingpong = prec == PREC_FP16_UMMA && !chain_mode() && fuse_rb_mode() && C[L] == 32 && out16_a == ws.a16[L];
+        GD_TRY(resblock(L, s0, n, wa, res_a, nullptr, out32_a, pingpong ? ws.t16[L] : out16_a, nullptr));
         if (last_l0) { ht_skip_is_head = true; ht_tail = true; }
+        if (pingpong) rb_in16 = ws.t16[L];
         return resblock(L, s0, n, wb, res_b, skip_b, out32_b, out16_b, s2d_b);
     };
     auto down_stage = [&](int L, int s0, int n) -> int {          // m_down{L+1} (ResUNet.py:32-34)
@@ -554,7 +578,7 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         GD_TRY(up_stage(0, s0, n));
     }
     // tail (ResUNet.py:39): conv(x + x1), times the per-stamp input scale
-    if (fuse) return launch_tail_gather(ws.tail_part, C[0] / 32, g[0], tscale, zout, nb, st);
+    if (fuse) return launch_tail_gather(ws.tail_part, (!chain_mode() && fuse_rb_mode() >= 2 && C[0] == 32) ? 2 : C[0] / 32, g[0], tscale, zout, nb, st);
     return launch_tail(ws.p32a[0], W->tail, C[0], g[0], tscale, zout, nb, st);
 }
 

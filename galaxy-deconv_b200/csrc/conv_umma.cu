@@ -377,6 +377,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
 static int g_num_sms = 0;
 static int g_l2pf = 0;
 static int g_bstages = 6;
+static int g_astages = 4;
 static int g_abl = 0;
 
 // Optional per-launch timing of k_conv_umma with CUDA events on the launching stream (gd_profile_begin/end):
@@ -409,12 +410,24 @@ int conv_profile_end(double* ms_total, double* flops_total, unsigned long long* 
     return GD_OK;
 }
 
+// Timing hook for the other tcgen05 conv kernels (conv_rb.cu): records the start event and returns the stop event to record.
+int conv_profile_mark(double flops, cudaStream_t st, cudaEvent_t* stop) {
+    *stop = nullptr;
+    if (!g_timing.on) return GD_OK;
+    cudaEvent_t e0 = g_timing.get();
+    *stop = g_timing.get();
+    g_timing.flops.push_back(flops);
+    GD_CUDA_CHECK(cudaEventRecord(e0, st));
+    return GD_OK;
+}
+
 int conv_umma_init() {
     int dev;
     GD_CUDA_CHECK(cudaGetDevice(&dev));
     GD_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     if (const char* e = getenv("GDECONV_L2PF")) g_l2pf = atoi(e);
     if (const char* e = getenv("GDECONV_ABL")) g_abl = atoi(e);
+    if (const char* e = getenv("GDECONV_ASTAGES")) { g_astages = atoi(e); if (g_astages < 2 || g_astages > MAX_A_STAGES) g_astages = 4; }
     if (const char* e = getenv("GDECONV_BSTAGES")) { g_bstages = atoi(e); if (g_bstages < 2 || g_bstages > MAX_B_STAGES) g_bstages = 6; }
 #define GD_UMMA_ATTR(J, KK)                                                                                                        \
     GD_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma<J, KK, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX)); \
@@ -459,7 +472,7 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
         if (b_region + 2 * (size_t)c.a_stage_bytes <= UMMA_SMEM_MAX || c.J == 1) break;
     }
     c.a_stages = (int)((UMMA_SMEM_MAX - b_region) / c.a_stage_bytes);
-    if (c.a_stages > MAX_A_STAGES) c.a_stages = MAX_A_STAGES;
+    if (c.a_stages > g_astages) c.a_stages = g_astages;
     if (c.a_stages < 2) { set_error("conv_umma: layer does not fit shared memory"); return GD_EUNSUPPORTED; }
     c.smem = (size_t)c.a_stages * c.a_stage_bytes + b_region;
     if (p.mode == 1) c.aux_off += c.a_stages * c.a_stage_bytes;     // relative to the start of dynamic smem

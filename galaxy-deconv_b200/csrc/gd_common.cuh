@@ -30,7 +30,7 @@ enum Precision { PREC_FP32_SIMT = GD_PREC_FP32_SIMT, PREC_FP16_UMMA = GD_PREC_FP
 // A feature map of C channels at resolution HxW for a chunk of B stamps is stored as
 //     act[C / CH][Ptot][CH]          CH = 8 for fp16, 4 for fp32  (one 16-byte vector per pixel and chunk)
 // where the pixel axis is a single linear index
-//     row(b, y, x) = base0 + b*S + y*Wp + x,   Wp = W+1,  S = (H+1)*Wp,  base0 = Wp+1
+//     row(b, y, x) = base0 + b*S + y*Wp + x,   Wp = W+1,  S = (H+1)*Wp,  base0 = Wp+1+64
 // i.e. every image row is followed by ONE zero pixel and every stamp by ONE zero row; those zeros are shared
 // by the neighbours on both sides, so the 3x3 tap (dy,dx) of ANY pixel is simply row + dy*Wp + dx and a conv
 // is a GEMM whose A operand for tap t is the same buffer shifted by a constant number of 16-byte rows.
@@ -55,12 +55,15 @@ GD_HD uint32_t div_by_magic(uint32_t n, uint32_t magic, uint32_t shift) { return
 
 inline Geom make_geom(int H, int batch) {
     Geom g;
-    g.H = H; g.W = H; g.Wp = H + 1; g.S = (H + 1) * (H + 1); g.base0 = g.Wp + 1;
+    // base0 >= Wp + 1 zero rows in front of the first stamp; 64 more so that the fused ResBlock kernel (conv_rb.cu), whose
+    // t window starts 64 rows before an item, never reads in front of the buffer
+    g.H = H; g.W = H; g.Wp = H + 1; g.S = (H + 1) * (H + 1); g.base0 = g.Wp + 1 + 64;
     div_magic((uint32_t)g.S, &g.magS, &g.shS); div_magic((uint32_t)g.Wp, &g.magW, &g.shW);
     g.M = batch * g.S;
     int mt = ((g.M + MTILE - 1) / MTILE + 7) / 8 * 8;
     // a CTA of the tcgen05 kernel owns up to 8 consecutive tiles and its window reaches Wp+1 rows past them
-    g.Ptot = mt * MTILE + 2 * g.base0 + MTILE;
+    // (conv_rb.cu: the x window of the last 384-row item ends up to 498 rows past M)
+    g.Ptot = mt * MTILE + 2 * g.base0 + 5 * MTILE;
     return g;
 }
 

@@ -14,6 +14,10 @@ size_t chain_flag_words(int max_rows);
 int launch_conv_chain(const ConvParams* layers, int nl, unsigned int* flags, cudaStream_t st);
 void conv_profile_begin();
 int conv_profile_end(double* ms_total, double* flops_total, unsigned long long* launches);
+int conv_profile_mark(double flops, cudaStream_t st, cudaEvent_t* stop);
+int conv_rb_init();
+bool conv_rb_supported(const ConvParams& p1, const ConvParams& p2);
+int launch_conv_rb(const ConvParams& p1, const ConvParams& p2, cudaStream_t st);
 
 int launch_g_prologue(const float* y, const float* psf, const float* alpha, float2* Pc, float* HtH, float* z, float* u,
                       float* x, int batch, cudaStream_t st);

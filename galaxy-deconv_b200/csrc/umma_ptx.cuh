@@ -14,7 +14,7 @@ constexpr int EPI_WARPS = 8;
 constexpr int MMA_WARPS = 4;                        // warps 1..4: MMA issuers, one 128-row tile of the item each (J <= 4)
 constexpr int EPI_WARP0 = 1 + MMA_WARPS;            // warps 5..12: epilogue
 constexpr int UMMA_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
-constexpr int MAX_A_STAGES = 4;
+constexpr int MAX_A_STAGES = 12;                    // upper bound; the default ring depth is 4 (GDECONV_ASTAGES): deeper rings measured slower
 constexpr int MAX_B_STAGES = 8;
 constexpr int TMEM_COLS = 512;                      // one CTA per SM owns all of TMEM: 2 accumulator stages x 256 columns
 constexpr int ACC_STAGE_COLS = 256;

@@ -1,7 +1,7 @@
 """Summarise the source page of one kernel of an .ncu-rep: per warp-role waits and top stall lines."""
 import csv, subprocess, sys, collections
 rep, kid = sys.argv[1], sys.argv[2]
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-id', kid], capture_output=True, text=True).stdout
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', *(['--kernel-id', kid] if ':' in kid else ['--launch-skip', kid, '--launch-count', '1'])], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}; data = rows[2:]
 S = lambda r: int(r[ix['# Samples']] or 0)
