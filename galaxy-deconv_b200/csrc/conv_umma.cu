@@ -25,6 +25,8 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <utility>
 #include <vector>
 
 namespace gd {
@@ -43,6 +45,7 @@ struct UmmaCfg {
     int nsl_log2, nb32_log2;   // log2(nslices), log2(ncta / 32): both are powers of two
     int abl;         // diagnostic ablation bits (GDECONV_ABL): 1 = no weight streaming, 2 = no epilogue global traffic, 4 = no activation loads
     int l2pf;        // producer prefetches the residual / skip rows of each item into L2
+    int cls;         // CTAs per cluster sharing every streamed weight stage by multicast (1 = no cluster)
     int aux_off;     // mode 1: byte offset of the 8 warp-private 4 KB transpose stages of epi_up_unit in dynamic shared memory
     size_t smem;
 };
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_A_STAGES; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), J); }
-        for (int s = 0; s < MAX_B_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), J); }
+        for (int s = 0; s < MAX_B_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), J * c.cls); }
         mbar_init(w_full, 1);
         const int nu_all = J * (c.ncta / 32);
         for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), J); mbar_init(acc_empty(s), nu_all >= 2 ? EPI_WARPS : EPI_WARPS / 2); }
@@ -105,13 +108,21 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
     }
     tc_fence_before();
     __syncthreads();
+    if (c.cls > 1) cluster_sync_all();             // the peers' barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
     const int nslabs = p.Kt / c.BK;
     const int chunks = c.BK / 8;
-    const int total_items = c.items_m * c.nslices;
     const int KC = p.Kt / 8;                       // K chunks per tap in the packed weights
+    // Work distribution.  Iteration `it` of the kernel-wide list is (M-group it >> nsl_log2, N-slice it & (nslices-1)); the
+    // CTAs of a cluster take the cls consecutive M-items of the group with the SAME slice, so they walk identical weight
+    // stage sequences in lockstep (cls = 1: one item per iteration).  M-items past items_m are dummies: no A loads, nothing stored.
+    const int cls = c.cls, rank = cls > 1 ? (int)cluster_ctarank() : 0;
+    const int it0 = (int)blockIdx.x / cls, it_stride = (int)gridDim.x / cls;
+    const int total_items = ((c.items_m + cls - 1) / cls) * c.nslices;
+    const uint16_t cmask = (uint16_t)((1u << cls) - 1);
+    auto item_m = [&](int it) { return (it >> c.nsl_log2) * cls + rank; };
 
     if (warp == 0) {
         // ===== producer: one thread issues every bulk copy =====
@@ -127,10 +138,11 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                     bulk_g2s(bdst + off, wts + off, (uint32_t)n, w_full);
                 }
             }
-            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-                const int im = item >> c.nsl_log2, ns = item & (c.nslices - 1);
+            for (int item = it0; item < total_items; item += it_stride) {
+                const int im = item_m(item), ns = item & (c.nslices - 1);
+                const bool dummy = im >= c.items_m;
                 const size_t row0 = (size_t)p.g.base0 + (size_t)im * J * MTILE - c.halo;
-                if (c.l2pf && p.mode == 0 && (p.res32 || p.skip32)) {
+                if (c.l2pf && p.mode == 0 && (p.res32 || p.skip32) && !dummy) {
                     // the epilogue of this item will read its residual / skip rows: pull them from HBM into L2 now
                     const size_t r0 = (size_t)p.g.base0 + (size_t)im * J * MTILE;
                     for (int pl = ns * (c.ncta / 4); pl < (ns + 1) * (c.ncta / 4); ++pl) {
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                 }
                 for (int s = 0; s < nslabs; ++s) {
                     mbar_wait(a_empty(as), aph ^ 1);
-                    if ((c.abl & 4) && aph) {
+                    if (((c.abl & 4) && aph) || dummy) {
                         mbar_arrive(a_full(as));                      // ablation: reuse whatever the stage holds
                     } else {
                         mbar_expect_tx(a_full(as), (uint32_t)c.a_stage_bytes);
@@ -158,10 +170,17 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                             } else {
                                 mbar_expect_tx(b_full(bs), (uint32_t)c.b_stage_bytes);
                                 const uint32_t bdst = smem_u32(b_smem + (size_t)bs * c.b_stage_bytes);
-                                for (int ch = 0; ch < chunks; ++ch)
-                                    bulk_g2s(bdst + (uint32_t)ch * c.ncta * 16,
-                                             wts + (((size_t)tap * KC + s * chunks + ch) * p.N + (size_t)ns * c.ncta) * 16,
-                                             (uint32_t)c.ncta * 16, b_full(bs));
+                                if (cls == 1) {
+                                    for (int ch = 0; ch < chunks; ++ch)
+                                        bulk_g2s(bdst + (uint32_t)ch * c.ncta * 16,
+                                                 wts + (((size_t)tap * KC + s * chunks + ch) * p.N + (size_t)ns * c.ncta) * 16,
+                                                 (uint32_t)c.ncta * 16, b_full(bs));
+                                } else {                        // this CTA fetches every cls-th chunk for the whole cluster
+                                    for (int ch = rank; ch < chunks; ch += cls)
+                                        bulk_g2s_mc(bdst + (uint32_t)ch * c.ncta * 16,
+                                                    wts + (((size_t)tap * KC + s * chunks + ch) * p.N + (size_t)ns * c.ncta) * 16,
+                                                    (uint32_t)c.ncta * 16, b_full(bs), cmask);
+                                }
                             }
                             if (++bs == c.b_stages) { bs = 0; bph ^= 1; }
                         }
@@ -188,7 +207,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
         const uint32_t a_kk = (2 * a_lbo) >> 4, b_kk = (2 * b_lbo) >> 4;
         const uint32_t ncta = (uint32_t)c.ncta;
         if (c.b_resident) mbar_wait(w_full, 0);
-        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        for (int item = it0; item < total_items; item += it_stride) {
             const int ns = item & (c.nslices - 1);
             mbar_wait(acc_empty(acs), accph ^ 1);
             tc_fence_after();
@@ -209,7 +228,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                     const uint64_t ad_t = ad_s + (uint64_t)(int64_t)p.off[tap];
                     tc_mma_tap<1, KK>(dcol + (uint32_t)jw * ncta, ncta, ad_t + (uint64_t)(jw * MTILE), bd, a_kk, b_kk, idesc, (uint32_t)((s | tap) != 0));
                     if (!c.b_resident) {
-                        tc_commit_pred(b_empty(bs), leader);
+                        if (cls == 1) tc_commit_pred(b_empty(bs), leader); else tc_commit_mc_pred(b_empty(bs), cmask);
                         if (++bs == c.b_stages) { bs = 0; bph ^= 1; }
                     }
                 }
@@ -240,7 +259,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
             auto unit_of = [&](int i) { return nu == 1 ? 0 : half + 2 * i; };
             auto issue_res = [&](int item, int i) {
                 if (EPI == EPI_PLAIN || !p.res32 || p.mode == 1 || i >= UPW_PREF || (c.abl & 2)) return;
-                const int im = item >> c.nsl_log2, ns = item & (c.nslices - 1);
+                const int im = item_m(item), ns = item & (c.nslices - 1);
                 const int uu = unit_of(i), j = uu >> c.nb32_log2, b = uu & (nb32 - 1);
                 const int m = (im * J + j) * MTILE + q * 32 + lane;
                 if (m >= g.M) return;
@@ -252,15 +271,15 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                     d[4 * k] = t.x; d[4 * k + 1] = t.y; d[4 * k + 2] = t.z; d[4 * k + 3] = t.w;
                 }
             };
-            int item = blockIdx.x;
+            int item = it0;
             if (item < total_items) {
 #pragma unroll
                 for (int i = 0; i < UPW_MAX; ++i)
                     if (i < upw || (nu == 1 && i == 0)) issue_res(item, i);
             }
-            for (; item < total_items; item += gridDim.x) {
-                const int im = item >> c.nsl_log2, ns = item & (c.nslices - 1);
-                const int nitem = item + gridDim.x;
+            for (; item < total_items; item += it_stride) {
+                const int im = item_m(item), ns = item & (c.nslices - 1);
+                const int nitem = item + it_stride;
                 mbar_wait(acc_full(acs), accph);
                 tc_fence_after();
 #pragma unroll
@@ -368,6 +387,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
     }
     tc_fence_before();
     __syncthreads();
+    if (c.cls > 1) cluster_sync_all();             // no CTA leaves while a peer may still multicast into it or signal its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
@@ -375,6 +395,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
 }
 
 static int g_num_sms = 0;
+static int g_cluster = 4;
 static int g_l2pf = 0;
 static int g_bstages = 6;
 static int g_astages = 4;
@@ -427,6 +448,7 @@ int conv_umma_init() {
     GD_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     if (const char* e = getenv("GDECONV_L2PF")) g_l2pf = atoi(e);
     if (const char* e = getenv("GDECONV_ABL")) g_abl = atoi(e);
+    if (const char* e = getenv("GDECONV_CLUSTER")) { g_cluster = atoi(e); if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4 && g_cluster != 8) g_cluster = 4; }
     if (const char* e = getenv("GDECONV_ASTAGES")) { g_astages = atoi(e); if (g_astages < 2 || g_astages > MAX_A_STAGES) g_astages = 4; }
     if (const char* e = getenv("GDECONV_BSTAGES")) { g_bstages = atoi(e); if (g_bstages < 2 || g_bstages > MAX_B_STAGES) g_bstages = 6; }
 #define GD_UMMA_ATTR(J, KK)                                                                                                        \
@@ -480,6 +502,7 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     c.items_m = (tiles + c.J - 1) / c.J;
     c.l2pf = g_l2pf;
     c.abl = g_abl;
+    c.cls = (!c.b_resident && (c.BK / 8) % g_cluster == 0) ? g_cluster : 1;
     auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
     c.nsl_log2 = ilog2(c.nslices); c.nb32_log2 = ilog2(c.ncta / 32);
     if ((1 << c.nsl_log2) != c.nslices || (1 << c.nb32_log2) != c.ncta / 32) { set_error("conv_umma: N=%d must split into power-of-two slices", p.N); return GD_EUNSUPPORTED; }
@@ -493,8 +516,8 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t st) {
     int rc = make_cfg(p, &c);
     if (rc != GD_OK) return rc;
     if (!g_num_sms) { set_error("conv_umma: library not initialised"); return GD_ECUDA; }
-    const int items = c.items_m * c.nslices;
-    const int grid = items < g_num_sms ? items : g_num_sms;
+    const int iters = ((c.items_m + c.cls - 1) / c.cls) * c.nslices;              // kernel-wide iteration list (see k_conv_umma)
+    int grid = (iters < g_num_sms / c.cls ? iters : g_num_sms / c.cls) * c.cls;   // cls > 1: refined below by the cluster occupancy
     cudaEvent_t e1 = nullptr;
     if (g_timing.on) {
         cudaEvent_t e0 = g_timing.get();
@@ -506,10 +529,36 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t st) {
     const int KK = c.BK / 16;
     const bool ht = p.head_t || p.tail_part;
     const bool plain = p.mode == 0 && !p.res32 && !p.skip32 && !p.out32 && !p.s2d && p.out16 && !ht;
+    // Launch helper: plain launch, or (streamed weights) clusters of c.cls CTAs with as many clusters as can be co-resident
+    auto go = [&](auto kern, auto hw) -> int {
+        if (c.cls == 1) { kern<<<grid, UMMA_THREADS, c.smem, st>>>(p, c, hw); return GD_OK; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(UMMA_THREADS); cfg.dynamicSmemBytes = c.smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)c.cls; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        static std::map<std::pair<const void*, int>, int> max_clusters;      // per (kernel, cluster size)
+        auto key = std::make_pair((const void*)kern, c.cls);
+        auto it = max_clusters.find(key);
+        if (it == max_clusters.end()) {
+            int n = 0;
+            cfg.gridDim = dim3((unsigned)(g_num_sms / c.cls * c.cls));
+            GD_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+            if (n < 1) { set_error("conv_umma: no cluster of %d CTAs fits", c.cls); return GD_ECUDA; }
+            it = max_clusters.emplace(key, n).first;
+        }
+        const int clusters = iters < it->second ? iters : it->second;
+        cfg.gridDim = dim3((unsigned)(clusters * c.cls));
+        GD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p, c, hw));
+        return GD_OK;
+    };
 #define GD_UMMA_GO(JJ, KKK)                                                                         \
     if (c.J == JJ && KK == KKK && !ht) {                                                            \
-        if (plain) k_conv_umma<JJ, KKK, EPI_PLAIN><<<grid, UMMA_THREADS, c.smem, st>>>(p, c, HtWeights<EPI_PLAIN, 128 / JJ>()); \
-        else k_conv_umma<JJ, KKK, EPI_FULL><<<grid, UMMA_THREADS, c.smem, st>>>(p, c, HtWeights<EPI_FULL, 128 / JJ>());         \
+        int rc2;                                                                                    \
+        if (plain) rc2 = go(k_conv_umma<JJ, KKK, EPI_PLAIN>, HtWeights<EPI_PLAIN, 128 / JJ>());     \
+        else rc2 = go(k_conv_umma<JJ, KKK, EPI_FULL>, HtWeights<EPI_FULL, 128 / JJ>());             \
+        if (rc2 != GD_OK) return rc2;                                                               \
     } else
 #define GD_UMMA_GO_HT(JJ, KKK)                                                                      \
     if (c.J == JJ && KK == KKK && ht && p.N == 128 / JJ) {                                          \

@@ -59,6 +59,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
+// Cluster multicast: the copy lands at the same shared-memory offset of every CTA in `mask` and completes tx bytes on the
+// mbarrier at the same offset of each of them.
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -90,6 +101,11 @@ __device__ __forceinline__ void tc_mma_f16_pred(uint32_t d_tmem, uint64_t adesc,
 }
 __device__ __forceinline__ void tc_commit_pred(uint32_t bar, uint32_t) {
     if (elect_one()) tc_commit(bar);
+}
+// completion of this thread's MMAs arrives on the barrier at the same offset of every CTA in `mask` (cluster-shared weight stages)
+__device__ __forceinline__ void tc_commit_mc_pred(uint32_t bar, uint16_t mask) {
+    if (elect_one())
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 // accumulate variant with a constant-true predicate (no register -> uniform-predicate shuffling in SASS)
 __device__ __forceinline__ void tc_mma_f16_acc(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
