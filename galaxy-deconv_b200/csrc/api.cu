@@ -344,7 +344,7 @@ struct Ws {
     float* HtH;                                // G only
     // ResUNet activations
     float *skip32[4], *p32a[4], *p32b[4];
-    void *a16[4], *t16[4], *d16[4];
+    void *a16[4], *t16[4], *d16[4], *lo16[4];   // lo16: fp16 correction planes of the hi/lo residual stream (hi = a16 / t16)
     unsigned int* chain_flags;                 // per-(layer, item) completion counters of the layer-chained kernel
     float *tpad, *tail_part;                   // head/tail fusion (conv_umma.cu EPI_HT): padded-linear input, per-tap tail sums
 };
@@ -377,6 +377,7 @@ static Ws ws_layout(unsigned char* base, int arch, int prec, int chunk) {
         if (L < 3) w.p32b[L] = (float*)take(n * 4);
         w.a16[L] = take(n * es);
         w.t16[L] = take(n * es);
+        w.lo16[L] = take(n * es);
         if (L > 0) w.d16[L] = take((size_t)2 * n * es);        // 4*C_{L-1} = 2*C_L channels
     }
     w.chain_flags = (unsigned int*)take(chain_flag_words(w.g[0].Ptot) * sizeof(unsigned int));
@@ -461,6 +462,15 @@ static int fuse_rb_mode() {
     }
     return g_fuse_rb;
 }
+// fp16 hi/lo residual stream on the tcgen05 path (ConvParams::res_hi); GDECONV_HILO=0 restores the fp32 stream buffers.
+static int g_hilo = -1;
+static int hilo_mode() {
+    if (g_hilo < 0) {
+        const char* e = getenv("GDECONV_HILO");
+        g_hilo = e ? atoi(e) : 1;
+    }
+    return g_hilo;
+}
 static int g_subchunk = 0;
 static int subchunk_size() {
     if (!g_subchunk) {
@@ -481,6 +491,7 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
     };
     // tcgen05 path: x1 is never stored in fp32; its consumers recompute it from tpad (ConvParams::head_t)
     const bool fuse = prec == PREC_FP16_UMMA && !chain_mode() && fuse_ht_mode() && C[0] <= 64;
+    const bool hilo = prec == PREC_FP16_UMMA && !chain_mode() && hilo_mode();
     {   // head (ResUNet.py:31): x1 = conv(t)  -> skip32[0] (fp32) + a16[0]
         ConvParams p = conv_base(g[0], nb);
         p.N = C[0]; p.out32 = fuse ? nullptr : ws.skip32[0]; p.out16 = ws.a16[0];
@@ -515,6 +526,13 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         if (ht_tail) { p[1].tail_part = at4(ws.tail_part, s0); p[1].tail_w = W->tail_h; p[1].out32 = nullptr; p[1].out16 = nullptr; }
         ht_res_is_head = ht_skip_is_head = ht_tail = false;
         rb_in16 = nullptr;
+        if (hilo) {           // stream values travel as fp16 hi (= the ResBlock's fp16 input / output) + fp16 lo
+            auto is_stream = [&](const float* q) {
+                return q && (q == (const float*)at(ws.p32a[L], L, s0) || (L < 3 && q == (const float*)at(ws.p32b[L], L, s0)));
+            };
+            if (is_stream(p[1].res32)) { p[1].res_hi = p[0].a; p[1].res_lo = at(ws.lo16[L], L, s0); p[1].res32 = nullptr; }
+            if (is_stream(p[1].out32) && p[1].out16) { p[1].out_lo = at(ws.lo16[L], L, s0); p[1].out32 = nullptr; }
+        }
         if (prec == PREC_FP16_UMMA && chain_mode() && C[L] == 64) return launch_conv_chain(p, 2, ws.chain_flags, st);
         // fused kernel, except (mode 1) for the ResBlock that ends in the m_tail partial sums: its FMA-heavy epilogue is
         // faster on the eight 32-channel epilogue warps of conv_umma.cu (profiles/README); GDECONV_FUSE_RB=2 fuses it too
@@ -555,6 +573,7 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         p.ntaps = 1; p.off[0] = 0; p.Kt = C[L + 1]; p.N = 4 * C[L]; p.a = at(ws.a16[L + 1], L + 1, s0); p.w = W->up[L];
         p.mode = 1; p.Cf = C[L]; p.Cf_log2 = 0; while ((1 << p.Cf_log2) < p.Cf) ++p.Cf_log2; p.gf = g[L]; p.gf.M = n * g[L].S;
         p.out32 = (float*)at(ws.p32a[L], L, s0); p.out16 = at(ws.a16[L], L, s0);
+        if (hilo) { p.out_lo = at(ws.lo16[L], L, s0); p.out32 = nullptr; }
         GD_TRY(run_conv(p, prec, st));
         if (L > 0) return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L],
                                         ws.skip32[L], nullptr, ws.a16[L], nullptr);

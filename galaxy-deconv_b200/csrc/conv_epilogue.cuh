@@ -151,6 +151,24 @@ __device__ __forceinline__ uint4 pack8_half(const float* v) {
     return u;
 }
 
+// hi/lo split of 8 fp32 values: hi = rn16(v), lo = rn16(v - hi)
+__device__ __forceinline__ void split8_hilo(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __half2 hh = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * k] - hf.x, v[2 * k + 1] - hf.y);
+        h[k] = *reinterpret_cast<const uint32_t*>(&hh); l[k] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]); lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// out[0..1] = float(hi) + float(lo) of one packed pair
+__device__ __forceinline__ float2 hilo_pair(uint32_t hi, uint32_t lo) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi)), b = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+    return make_float2(a.x + b.x, a.y + b.y);
+}
+
 // v[16] = relu?(acc) + r  ->  out32 / out16 / s2d   (same arithmetic order as epilogue_store16: (acc + res) + skip
 // differs only by association of res + skip, which the fp32 validation mode does not use)
 __device__ __forceinline__ void epi_store16_half(const ConvParams& p, const RowCtx& rc, const EpiAddr& a, int n0, float* v,
@@ -185,6 +203,20 @@ __device__ __forceinline__ void epi_store16_half(const ConvParams& p, const RowC
 
 // stores only (all arithmetic already applied): out32 / out16 / s2d of one 16-column group
 __device__ __forceinline__ void epi_out16(const ConvParams& p, const RowCtx& rc, const EpiAddr& a, int n0, const float* v) {
+    if (p.out_lo) {           // fp16 hi/lo stream: hi -> out16 (the operand copy), lo -> out_lo
+        uint4 h0, l0, h1, l1;
+        split8_hilo(v, h0, l0); split8_hilo(v + 8, h1, l1);
+        uint4* oh = reinterpret_cast<uint4*>(p.out16) + (size_t)(a.c0 / 8) * a.Ptot + a.row;
+        uint4* ol = reinterpret_cast<uint4*>(p.out_lo) + (size_t)(a.c0 / 8) * a.Ptot + a.row;
+        oh[0] = h0; oh[(size_t)a.Ptot] = h1; ol[0] = l0; ol[(size_t)a.Ptot] = l1;
+        if (p.s2d) {
+            uint4* base = reinterpret_cast<uint4*>(p.s2d);
+            const int cb = rc.ctap * p.N + n0;
+            base[(size_t)(cb / 8) * p.gc.Ptot + rc.crow] = h0;
+            base[(size_t)(cb / 8 + 1) * p.gc.Ptot + rc.crow] = h1;
+        }
+        return;
+    }
     if (p.out32) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -234,6 +266,18 @@ __device__ __forceinline__ void epi_up_unit(const ConvParams& p, bool valid, int
 #pragma unroll
         for (int g = 0; g < 4; ++g) x[g] = stage[8 * src + ((dx * 4 + g) ^ (src & 7))];
         if (ok) {
+            if (p.out_lo) {                      // fp16 hi/lo stream
+                uint4* oh = reinterpret_cast<uint4*>(p.out16) + (size_t)(c0 >> 3) * Pf + row;
+                uint4* ol = reinterpret_cast<uint4*>(p.out_lo) + (size_t)(c0 >> 3) * Pf + row;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float a[8] = {x[2 * h].x, x[2 * h].y, x[2 * h].z, x[2 * h].w, x[2 * h + 1].x, x[2 * h + 1].y, x[2 * h + 1].z, x[2 * h + 1].w};
+                    uint4 hi, lo;
+                    split8_hilo(a, hi, lo);
+                    oh[(size_t)h * Pf] = hi; ol[(size_t)h * Pf] = lo;
+                }
+                continue;
+            }
             if (p.out32) {
                 float4* o = reinterpret_cast<float4*>(p.out32) + (size_t)(c0 >> 2) * Pf + row;
 #pragma unroll

@@ -231,9 +231,21 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_rb_umma(const ConvParams p1
         const uint32_t Ptot = (uint32_t)g.Ptot;
         float add[RB_J2][16];
         auto issue_res = [&](int im, int j) {
-            if (!p2.res32) return;
+            if (!p2.res32 && !p2.res_hi) return;
             const int m = im * RB_R + j * MTILE + q * 32 + lane;
             if (m >= g.M) return;
+            if (p2.res_hi) {                     // fp16 hi/lo stream: raw packed halves (add[j][0..7] = hi, [8..15] = lo), decoded at use
+                const size_t o = (size_t)(c0 >> 3) * Ptot + (g.base0 + m);
+                const uint4* sh = reinterpret_cast<const uint4*>(p2.res_hi) + o;
+                const uint4* sl = reinterpret_cast<const uint4*>(p2.res_lo) + o;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint4 t = __ldg(sh + (size_t)k * Ptot), u = __ldg(sl + (size_t)k * Ptot);
+                    add[j][4 * k] = __uint_as_float(t.x); add[j][4 * k + 1] = __uint_as_float(t.y); add[j][4 * k + 2] = __uint_as_float(t.z); add[j][4 * k + 3] = __uint_as_float(t.w);
+                    add[j][8 + 4 * k] = __uint_as_float(u.x); add[j][9 + 4 * k] = __uint_as_float(u.y); add[j][10 + 4 * k] = __uint_as_float(u.z); add[j][11 + 4 * k] = __uint_as_float(u.w);
+                }
+                return;
+            }
             const float4* src = reinterpret_cast<const float4*>(p2.res32) + (size_t)(c0 >> 2) * Ptot + (g.base0 + m);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -275,7 +287,13 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_rb_umma(const ConvParams p1
 #pragma unroll
                     for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
                 }
-                if (p2.res32 && m < g.M) {
+                if (p2.res_hi && m < g.M) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float2 f = hilo_pair(__float_as_uint(add[j][k]), __float_as_uint(add[j][8 + k]));
+                        v[2 * k] += f.x; v[2 * k + 1] += f.y;
+                    }
+                } else if (p2.res32 && m < g.M) {
 #pragma unroll
                     for (int k = 0; k < 16; ++k) v[k] += add[j][k];
                 }

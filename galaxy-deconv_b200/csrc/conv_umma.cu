@@ -258,16 +258,28 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
             // row decomposition of GEMM row m: validity + absolute row (+ s2d / pixel-shuffle targets via make_row_ctx)
             auto unit_of = [&](int i) { return nu == 1 ? 0 : half + 2 * i; };
             auto issue_res = [&](int item, int i) {
-                if (EPI == EPI_PLAIN || !p.res32 || p.mode == 1 || i >= UPW_PREF || (c.abl & 2)) return;
+                if (EPI == EPI_PLAIN || (!p.res32 && !p.res_hi) || p.mode == 1 || i >= UPW_PREF || (c.abl & 2)) return;
                 const int im = item_m(item), ns = item & (c.nslices - 1);
                 const int uu = unit_of(i), j = uu >> c.nb32_log2, b = uu & (nb32 - 1);
                 const int m = (im * J + j) * MTILE + q * 32 + lane;
                 if (m >= g.M) return;
+                float* d = add[EPI != EPI_PLAIN && i < UPW_PREF ? i : 0];
+                if (p.res_hi) {                  // fp16 hi/lo stream: raw packed halves, decoded at use (d[0..15] = hi, d[16..31] = lo)
+                    const size_t o = (size_t)((ns * c.ncta + b * 32) >> 3) * Ptot + (g.base0 + m);
+                    const uint4* sh = reinterpret_cast<const uint4*>(p.res_hi) + o;
+                    const uint4* sl = reinterpret_cast<const uint4*>(p.res_lo) + o;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint4 t = __ldg(sh + (size_t)k * Ptot), u = __ldg(sl + (size_t)k * Ptot);
+                        d[4 * k] = __uint_as_float(t.x); d[4 * k + 1] = __uint_as_float(t.y); d[4 * k + 2] = __uint_as_float(t.z); d[4 * k + 3] = __uint_as_float(t.w);
+                        d[16 + 4 * k] = __uint_as_float(u.x); d[17 + 4 * k] = __uint_as_float(u.y); d[18 + 4 * k] = __uint_as_float(u.z); d[19 + 4 * k] = __uint_as_float(u.w);
+                    }
+                    return;
+                }
                 const float4* src = reinterpret_cast<const float4*>(p.res32) + (size_t)((ns * c.ncta + b * 32) >> 2) * Ptot + (g.base0 + m);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     float4 t = __ldg(src + (size_t)k * Ptot);
-                    float* d = add[EPI != EPI_PLAIN && i < UPW_PREF ? i : 0];
                     d[4 * k] = t.x; d[4 * k + 1] = t.y; d[4 * k + 2] = t.z; d[4 * k + 3] = t.w;
                 }
             };
@@ -330,7 +342,27 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
 #pragma unroll
                             for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
                         }
-                        if (p.res32 && p.mode == 0 && m < g.M && !(c.abl & 2)) {
+                        if (p.res_hi && p.mode == 0 && m < g.M && !(c.abl & 2)) {
+                            if (i < UPW_PREF) {
+                                const float* d = add[EPI != EPI_PLAIN && i < UPW_PREF ? i : 0];
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) {
+                                    const float2 f = hilo_pair(__float_as_uint(d[k]), __float_as_uint(d[16 + k]));
+                                    v[2 * k] += f.x; v[2 * k + 1] += f.y;
+                                }
+                            } else {
+                                const size_t o = (size_t)(n0 >> 3) * Ptot + (g.base0 + m);
+                                const uint4* sh = reinterpret_cast<const uint4*>(p.res_hi) + o;
+                                const uint4* sl = reinterpret_cast<const uint4*>(p.res_lo) + o;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint4 t = __ldg(sh + (size_t)k * Ptot), u = __ldg(sl + (size_t)k * Ptot);
+                                    const float2 f0 = hilo_pair(t.x, u.x), f1 = hilo_pair(t.y, u.y), f2 = hilo_pair(t.z, u.z), f3 = hilo_pair(t.w, u.w);
+                                    v[8 * k] += f0.x; v[8 * k + 1] += f0.y; v[8 * k + 2] += f1.x; v[8 * k + 3] += f1.y;
+                                    v[8 * k + 4] += f2.x; v[8 * k + 5] += f2.y; v[8 * k + 6] += f3.x; v[8 * k + 7] += f3.y;
+                                }
+                            }
+                        } else if (p.res32 && p.mode == 0 && m < g.M && !(c.abl & 2)) {
                             if (i < UPW_PREF) {
 #pragma unroll
                                 for (int k = 0; k < 32; ++k) v[k] += add[EPI != EPI_PLAIN && i < UPW_PREF ? i : 0][k];
@@ -528,7 +560,7 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t st) {
     }
     const int KK = c.BK / 16;
     const bool ht = p.head_t || p.tail_part;
-    const bool plain = p.mode == 0 && !p.res32 && !p.skip32 && !p.out32 && !p.s2d && p.out16 && !ht;
+    const bool plain = p.mode == 0 && !p.res32 && !p.res_hi && !p.out_lo && !p.skip32 && !p.out32 && !p.s2d && p.out16 && !ht;
     // Launch helper: plain launch, or (streamed weights) clusters of c.cls CTAs with as many clusters as can be co-resident
     auto go = [&](auto kern, auto hw) -> int {
         if (c.cls == 1) { kern<<<grid, UMMA_THREADS, c.smem, st>>>(p, c, hw); return GD_OK; }

@@ -95,6 +95,12 @@ struct ConvParams {
     int Cf, Cf_log2;
     Geom gc;                  // coarse level (s2d target)
     Geom gf;                  // fine level (mode 1 target)
+    // fp16 hi/lo residual stream (tcgen05 path).  A stream value x is kept as hi = rn16(x) -- which IS the fp16 operand copy
+    // the next conv reads -- plus lo = rn16(x - hi) in a second fp16 buffer: 4 bytes per element written instead of 4 (fp32
+    // stream) + 2 (operand copy), |x - (hi + lo)| <= 2^-22 |x|.  Layout of both: [N/8][Ptot][8] like every fp16 activation.
+    const void* res_hi;       // += float(res_hi) + float(res_lo)   (instead of res32)
+    const void* res_lo;
+    void* out_lo;             // out16 receives hi, out_lo receives lo   (instead of out32)
     // head / tail fusion (tcgen05 path, level 0 only; conv_umma.cu EPI_HT).  The fp32 output of m_head (ResUNet.py:31)
     // is never stored: wherever it is consumed as a residual or as the final U-Net skip (ResUNet.py:39) the epilogue
     // recomputes it from the 1-channel padded-linear input `head_t` (9 FMAs per channel).  The last conv of m_up1 does
