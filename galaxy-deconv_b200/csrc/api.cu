@@ -495,7 +495,7 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
     {   // head (ResUNet.py:31): x1 = conv(t)  -> skip32[0] (fp32) + a16[0]
         ConvParams p = conv_base(g[0], nb);
         p.N = C[0]; p.out32 = fuse ? nullptr : ws.skip32[0]; p.out16 = ws.a16[0];
-        GD_TRY(launch_head(t, W->head, C[0], p, nb, prec, fuse ? ws.tpad : nullptr, st));
+        GD_TRY(launch_head(t, W->head, C[0] <= 64 ? W->head_h : nullptr, C[0], p, nb, prec, fuse ? ws.tpad : nullptr, st));
     }
     auto at4 = [&](float* base, int s0) -> float* { return base + (size_t)s0 * g[0].S; };    // 4-byte rows of level 0
     // one ResBlock (resnet_basicblock.py:69-71) on stamps [s0, s0+n): stream + conv(relu(conv(stream))) -> two layers
@@ -534,10 +534,11 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
             if (is_stream(p[1].out32) && p[1].out16) { p[1].out_lo = at(ws.lo16[L], L, s0); p[1].out32 = nullptr; }
         }
         if (prec == PREC_FP16_UMMA && chain_mode() && C[L] == 64) return launch_conv_chain(p, 2, ws.chain_flags, st);
-        // fused kernel, except (mode 1) for the ResBlock that ends in the m_tail partial sums: its FMA-heavy epilogue is
-        // faster on the eight 32-channel epilogue warps of conv_umma.cu (profiles/README); GDECONV_FUSE_RB=2 fuses it too
+        // fused kernel, except (mode 1) for the two ResBlocks whose epilogue recomputes m_head / reduces against m_tail: those
+        // FMA-heavy epilogues are faster on the eight 32-channel epilogue warps of conv_umma.cu (profiles/README);
+        // GDECONV_FUSE_RB=2 fuses them too
         if (prec == PREC_FP16_UMMA && !chain_mode() && fuse_rb_mode() && conv_rb_supported(p[0], p[1]) &&
-            (fuse_rb_mode() >= 2 || !p[1].tail_part))
+            (fuse_rb_mode() >= 2 || (!p[1].tail_part && !p[1].head_t)))
             return launch_conv_rb(p[0], p[1], st);
         if (p[0].a == p[0].out16 || p[1].a == p[1].out16) GD_FAIL(GD_EUNSUPPORTED, "resblock: in-place fp16 buffers need the fused kernel");
         GD_TRY(run_conv(p[0], prec, st));
@@ -553,8 +554,11 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
             return launch_conv_chain(p, 4, ws.chain_flags, st);
         }
         const bool last_l0 = fuse && L == 0 && skip_b != nullptr;       // second ResBlock of m_up1: + x1, then m_tail
-        if (fuse && L == 0 && res_a == ws.skip32[0]) ht_res_is_head = true;   // first ResBlock of m_down1: residual = x1
-        const bool pingpong = prec == PREC_FP16_UMMA && !chain_mode() && fuse_rb_mode() && C[L] == 32 && out16_a == ws.a16[L];
+        const bool first_ht = fuse && L == 0 && res_a == ws.skip32[0];        // first ResBlock of m_down1: residual = x1
+        if (first_ht) ht_res_is_head = true;
+        // the first ResBlock writes its fp16 output to t16 when it runs in the fused kernel (no in-place halo race)
+        const bool pingpong = prec == PREC_FP16_UMMA && !chain_mode() && fuse_rb_mode() && C[L] == 32 && out16_a == ws.a16[L] &&
+                              (fuse_rb_mode() >= 2 || !first_ht);
         GD_TRY(resblock(L, s0, n, wa, res_a, nullptr, out32_a, pingpong ? ws.t16[L] : out16_a, nullptr));
         if (last_l0) { ht_skip_is_head = true; ht_tail = true; }
         if (pingpong) rb_in16 = ws.t16[L];

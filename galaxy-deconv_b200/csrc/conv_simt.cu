@@ -9,6 +9,8 @@
 #include "kernels.cuh"
 #include "launch.cuh"
 
+#include <cstring>
+
 namespace gd {
 
 constexpr int SIMT_KSLAB = 256;
@@ -108,6 +110,37 @@ __global__ void __launch_bounds__(128) k_head(const float* __restrict__ t, const
     }
 }
 
+// Product-path head for C0 = 32 (tcgen05 path with head/tail fusion): only the fp16 operand copy and the padded-linear copy
+// of the input are written (the fp32 head output is recomputed where it is consumed).  The 288 weights are kernel
+// parameters, i.e. immediate constant-bank operands of the FFMAs -- the generic k_head is bound by its shared-memory loads.
+struct HeadW32 { float w[9 * 32]; };
+__global__ void __launch_bounds__(128) k_head32(const float* __restrict__ t, const __grid_constant__ HeadW32 hw, Geom g, __half* __restrict__ out16,
+                                                float* __restrict__ tpad, int batch) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * NPIX) return;
+    const int b = idx / NPIX, r = idx - b * NPIX, y = r / STAMP, x = r - y * STAMP;
+    float in[9];
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int yy = y + dy, xx = x + dx;
+            in[(dy + 1) * 3 + dx + 1] = (yy >= 0 && yy < STAMP && xx >= 0 && xx < STAMP) ? __ldg(t + (size_t)b * NPIX + yy * STAMP + xx) : 0.f;
+        }
+    const int row = g.base0 + b * g.S + y * g.Wp + x;
+    tpad[row] = in[4];
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = fmaf(in[tp], hw.w[tp * 32 + c], acc[c]);
+    uint4* dst = reinterpret_cast<uint4*>(out16) + row;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[(size_t)k * g.Ptot] = pack8_half(acc + 8 * k);
+}
+
 // tail: x32 [C0/4][Ptot][4] fp32 -> z [B][48*48] fp32, times the per-stamp power-of-two scale.
 // Works in the padded-linear row space (the halo rows of the stream are zero, so there are no bounds checks): a CTA
 // stages the window rows [m0 - Wp - 1, m0 + TAIL_ROWS + Wp + 1) of all C0/4 planes in shared memory with coalesced
@@ -173,9 +206,16 @@ int launch_conv_simt(const ConvParams& p, int prec, cudaStream_t st) {
     return GD_OK;
 }
 
-int launch_head(const float* t, const float* w, int C0, const ConvParams& p, int batch, int prec, float* tpad, cudaStream_t st) {
+int launch_head(const float* t, const float* w, const float* w_host, int C0, const ConvParams& p, int batch, int prec, float* tpad, cudaStream_t st) {
     int n = batch * NPIX, blocks = (n + 127) / 128;
     if (n <= 0) return GD_OK;
+    if (prec == PREC_FP16_UMMA && C0 == 32 && tpad && !p.out32 && p.out16 && w_host) {
+        HeadW32 hw;
+        memcpy(hw.w, w_host, sizeof(hw.w));
+        k_head32<<<blocks, 128, 0, st>>>(t, hw, p.g, reinterpret_cast<__half*>(p.out16), tpad, batch);
+        GD_LAUNCHED();
+        return GD_OK;
+    }
     if (prec == PREC_FP32_SIMT) k_head<float><<<blocks, 128, 9 * C0 * sizeof(float), st>>>(t, w, C0, p, batch, tpad);
     else k_head<__half><<<blocks, 128, 9 * C0 * sizeof(float), st>>>(t, w, C0, p, batch, tpad);
     GD_LAUNCHED();
