@@ -55,6 +55,7 @@ struct GdWeights {
     const float* head;                // [9][C0] fp32
     const float* tail;                // [9][C0] fp32
     float head_h[9 * 64], tail_h[9 * 64];   // host copies (C0 <= 64): kernel-parameter weights of the head/tail-fused epilogue
+    float tail_head_g[81];                  // G[tap2][tap1] = sum_c tail[tap2][c] * head[tap1][c]: m_tail(m_head(t)) as one 1-channel stencil
     const void* down_rb[3][2][2];     // down stage L, ResBlock, conv  (3x3, C_L -> C_L)
     const void* down[3];              // k2s2 strided conv C_L -> C_{L+1}
     const void* body_rb[2][2];
@@ -218,6 +219,12 @@ extern "C" int gd_pack_weights(int arch, int n_iters, const GdTensorDesc* tensor
             for (int c = 0; c < C0; ++c)
                 for (int tp = 0; tp < 9; ++tp) { h[(size_t)tp * C0 + c] = th->data[(size_t)c * 9 + tp]; tl[(size_t)tp * C0 + c] = tt->data[(size_t)c * 9 + tp]; }
             if (C0 <= 64) { memcpy(W.head_h, h.data(), h.size() * sizeof(float)); memcpy(W.tail_h, tl.data(), tl.size() * sizeof(float)); }
+            for (int t2 = 0; t2 < 9; ++t2)
+                for (int t1 = 0; t1 < 9; ++t1) {
+                    double a = 0;
+                    for (int c = 0; c < C0; ++c) a += (double)tl[(size_t)t2 * C0 + c] * (double)h[(size_t)t1 * C0 + c];
+                    W.tail_head_g[t2 * 9 + t1] = (float)a;
+                }
             slot((const void**)&W.head, pack_f32(bl, h.data(), h.size()));
             slot((const void**)&W.tail, pack_f32(bl, tl.data(), tl.size()));
         }
@@ -471,6 +478,15 @@ static int hilo_mode() {
     }
     return g_hilo;
 }
+// m_tail(x1) as an 81-coefficient stencil of the denoiser input in k_tail_gather (GDECONV_TAILG=0: recompute x1 in the conv epilogue)
+static int g_tailg = -1;
+static int tail_g_mode() {
+    if (g_tailg < 0) {
+        const char* e = getenv("GDECONV_TAILG");
+        g_tailg = e ? atoi(e) : 1;
+    }
+    return g_tailg;
+}
 static int g_subchunk = 0;
 static int subchunk_size() {
     if (!g_subchunk) {
@@ -514,7 +530,7 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         if (s2d) { out[1].s2d = at(s2d, L + 1, s0); out[1].gc = g[L + 1]; out[1].gc.M = n * g[L + 1].S; }
     };
     // head/tail fusion hooks for the second conv of the next resblock() call (level 0, consumed once)
-    bool ht_res_is_head = false, ht_skip_is_head = false, ht_tail = false;
+    bool ht_res_is_head = false, ht_skip_is_head = false, ht_tail = false, ht_drop_skip = false;
     auto resblock = [&](int L, int s0, int n, const void* const* w2, const float* res, const float* skip, float* out32,
                         void* out16, void* s2d) -> int {
         ConvParams p[2];
@@ -523,8 +539,9 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
             p[1].head_t = at4(ws.tpad, s0); p[1].head_w = W->head_h;
             if (ht_res_is_head) p[1].res32 = nullptr; else p[1].skip32 = nullptr;
         }
+        if (ht_drop_skip) p[1].skip32 = nullptr;          // the U-Net skip x1 enters through the composite stencil of k_tail_gather
         if (ht_tail) { p[1].tail_part = at4(ws.tail_part, s0); p[1].tail_w = W->tail_h; p[1].out32 = nullptr; p[1].out16 = nullptr; }
-        ht_res_is_head = ht_skip_is_head = ht_tail = false;
+        ht_res_is_head = ht_skip_is_head = ht_tail = ht_drop_skip = false;
         rb_in16 = nullptr;
         if (hilo) {           // stream values travel as fp16 hi (= the ResBlock's fp16 input / output) + fp16 lo
             auto is_stream = [&](const float* q) {
@@ -560,7 +577,7 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         const bool pingpong = prec == PREC_FP16_UMMA && !chain_mode() && fuse_rb_mode() && C[L] == 32 && out16_a == ws.a16[L] &&
                               (fuse_rb_mode() >= 2 || !first_ht);
         GD_TRY(resblock(L, s0, n, wa, res_a, nullptr, out32_a, pingpong ? ws.t16[L] : out16_a, nullptr));
-        if (last_l0) { ht_skip_is_head = true; ht_tail = true; }
+        if (last_l0) { ht_skip_is_head = !tail_g_mode(); ht_tail = true; ht_drop_skip = tail_g_mode() != 0; }
         if (pingpong) rb_in16 = ws.t16[L];
         return resblock(L, s0, n, wb, res_b, skip_b, out32_b, out16_b, s2d_b);
     };
@@ -601,7 +618,8 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         GD_TRY(up_stage(0, s0, n));
     }
     // tail (ResUNet.py:39): conv(x + x1), times the per-stamp input scale
-    if (fuse) return launch_tail_gather(ws.tail_part, (!chain_mode() && fuse_rb_mode() >= 2 && C[0] == 32) ? 2 : C[0] / 32, g[0], tscale, zout, nb, st);
+    if (fuse) return launch_tail_gather(ws.tail_part, (!chain_mode() && fuse_rb_mode() >= 2 && C[0] == 32) ? 2 : C[0] / 32, g[0], tscale, zout, nb,
+                                        ws.tpad, tail_g_mode() ? W->tail_head_g : nullptr, st);
     return launch_tail(ws.p32a[0], W->tail, C[0], g[0], tscale, zout, nb, st);
 }
 

@@ -179,19 +179,45 @@ __global__ void __launch_bounds__(TAIL_ROWS) k_tail(const float* __restrict__ x3
     z[(size_t)b * NPIX + y * STAMP + x] = s * tscale[b];
 }
 
-// Tail of the head/tail-fused tcgen05 path: the last conv of m_up1 left P[u*9 + tap][row] = sum_c w_tail[tap][c] * (x + x1)[row][c]
-// (32-channel unit u); m_tail (ResUNet.py:39) is then z[m] = sum_tap sum_u P[u*9 + tap][m + off(tap)], times the per-stamp
-// power-of-two input scale.  Halo rows of P are never written (zero since gd_workspace_init).
+// Tail of the head/tail-fused tcgen05 path: the last conv of m_up1 left P[u*9 + tap][row] = sum_c w_tail[tap][c] * x[row][c]
+// (32-channel unit u, x = the ResBlock output WITHOUT the U-Net skip x1); m_tail (ResUNet.py:39) of x + x1 is then
+//     z[m] = sum_tap sum_u P[u*9 + tap][m + off(tap)]  +  tail(x1)[m],
+// times the per-stamp power-of-two input scale.  Since x1 = m_head(t) is linear in the 1-channel input t, its tail is the
+// 81-coefficient composite  tail(x1)[m] = sum_{tap2: m+off2 inside the stamp} sum_tap1 G[tap2][tap1] * t[m + off2 + off1],
+// G = W_tail W_head^T (kernel parameters), evaluated here from the padded-linear copy of t (zero halos) instead of 288 FMAs
+// per row in the conv epilogue.  `G == nullptr-like` (has_g = 0): P already contains x1.  Halo rows of P are never written.
+struct TailG { float g[81]; };
 __global__ void __launch_bounds__(256) k_tail_gather(const float* __restrict__ P, int units, Geom g, const float* __restrict__ tscale,
-                                                     float* __restrict__ z, int batch) {
+                                                     float* __restrict__ z, int batch, const float* __restrict__ tpad, int has_g,
+                                                     const __grid_constant__ TailG G) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= batch * NPIX) return;
     const int b = idx / NPIX, r = idx - b * NPIX, y = r / STAMP, x = r - y * STAMP;
-    const float* src = P + (g.base0 + b * g.S + y * g.Wp + x);
+    const int row = g.base0 + b * g.S + y * g.Wp + x;
+    const float* src = P + row;
     float s = 0.f;
     for (int u = 0; u < units; ++u) {
 #pragma unroll
         for (int t = 0; t < 9; ++t) s += __ldg(src + (size_t)(u * 9 + t) * g.Ptot + (t / 3 - 1) * g.Wp + (t % 3 - 1));
+    }
+    if (has_g) {
+        float tt[25];                             // 5x5 neighbourhood of t (zero outside the stamp)
+#pragma unroll
+        for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+            for (int dx = -2; dx <= 2; ++dx) {
+                const int yy = y + dy, xx = x + dx;
+                tt[(dy + 2) * 5 + dx + 2] = (yy >= 0 && yy < STAMP && xx >= 0 && xx < STAMP) ? __ldg(tpad + row + dy * g.Wp + dx) : 0.f;
+            }
+#pragma unroll
+        for (int t2 = 0; t2 < 9; ++t2) {
+            const int y2 = y + t2 / 3 - 1, x2 = x + t2 % 3 - 1;
+            if (y2 < 0 || y2 >= STAMP || x2 < 0 || x2 >= STAMP) continue;      // m_tail zero-pads x + x1
+            float a = 0.f;
+#pragma unroll
+            for (int t1 = 0; t1 < 9; ++t1) a = fmaf(G.g[t2 * 9 + t1], tt[(t2 / 3 + t1 / 3) * 5 + (t2 % 3 + t1 % 3)], a);
+            s += a;
+        }
     }
     z[idx] = s * tscale[b];
 }
@@ -222,9 +248,13 @@ int launch_head(const float* t, const float* w, const float* w_host, int C0, con
     return GD_OK;
 }
 
-int launch_tail_gather(const float* P, int units, const Geom& g, const float* tscale, float* z, int batch, cudaStream_t st) {
+int launch_tail_gather(const float* P, int units, const Geom& g, const float* tscale, float* z, int batch, const float* tpad,
+                       const float* G81_host, cudaStream_t st) {
     if (batch <= 0) return GD_OK;
-    k_tail_gather<<<(batch * NPIX + 255) / 256, 256, 0, st>>>(P, units, g, tscale, z, batch);
+    TailG G;
+    memset(&G, 0, sizeof(G));
+    if (G81_host) memcpy(G.g, G81_host, sizeof(G.g));
+    k_tail_gather<<<(batch * NPIX + 255) / 256, 256, 0, st>>>(P, units, g, tscale, z, batch, tpad, G81_host != nullptr, G);
     GD_LAUNCHED();
     return GD_OK;
 }

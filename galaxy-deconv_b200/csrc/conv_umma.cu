@@ -428,6 +428,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
 
 static int g_num_sms = 0;
 static int g_cluster = 4;
+static int g_jcols = 128;      // accumulator columns per item of the resident-weight 3x3 layers
+static int g_jcols1 = 128;     // ... of the 1-tap (k2s2) layers
 static int g_l2pf = 0;
 static int g_bstages = 6;
 static int g_astages = 4;
@@ -480,6 +482,8 @@ int conv_umma_init() {
     GD_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     if (const char* e = getenv("GDECONV_L2PF")) g_l2pf = atoi(e);
     if (const char* e = getenv("GDECONV_ABL")) g_abl = atoi(e);
+    if (const char* e = getenv("GDECONV_JCOLS")) { g_jcols = atoi(e) == 256 ? 256 : 128; }
+    if (const char* e = getenv("GDECONV_JCOLS1")) { g_jcols1 = atoi(e) == 256 ? 256 : 128; }
     if (const char* e = getenv("GDECONV_CLUSTER")) { g_cluster = atoi(e); if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4 && g_cluster != 8) g_cluster = 4; }
     if (const char* e = getenv("GDECONV_ASTAGES")) { g_astages = atoi(e); if (g_astages < 2 || g_astages > MAX_A_STAGES) g_astages = 4; }
     if (const char* e = getenv("GDECONV_BSTAGES")) { g_bstages = atoi(e); if (g_bstages < 2 || g_bstages > MAX_B_STAGES) g_bstages = 6; }
@@ -518,7 +522,7 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     }
     // resident weights: <= 128 accumulator columns per item (2 epilogue units per warp, fine-grained A ring, good tail
     // balance); streamed weights: 256 columns so that every weight stage is reused by twice as many rows
-    c.J = (c.b_resident ? 128 : ACC_STAGE_COLS) / c.ncta;
+    c.J = (c.b_resident ? (p.ntaps == 1 ? g_jcols1 : g_jcols) : ACC_STAGE_COLS) / c.ncta;
     if (c.J > 4) c.J = 4;
     for (;; c.J >>= 1) {
         c.win_rows = MTILE * c.J + 2 * c.halo;

@@ -44,7 +44,8 @@ int launch_subnet(const SubnetParams& P, const float* psf, const float* alpha, f
 int launch_conv_simt(const ConvParams& p, int prec, cudaStream_t st);
 int launch_conv_umma(const ConvParams& p, cudaStream_t st);
 int launch_head(const float* t, const float* w, const float* w_host, int C0, const ConvParams& p, int batch, int prec, float* tpad, cudaStream_t st);
-int launch_tail_gather(const float* P, int units, const Geom& g, const float* tscale, float* z, int batch, cudaStream_t st);
+int launch_tail_gather(const float* P, int units, const Geom& g, const float* tscale, float* z, int batch, const float* tpad,
+                       const float* G81_host, cudaStream_t st);
 int launch_tail(const float* x32, const float* w, int C0, const Geom& g, const float* tscale, float* z, int batch,
                 cudaStream_t st);
 

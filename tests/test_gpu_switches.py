@@ -1,0 +1,65 @@
+"""Every A/B switch of the tcgen05 denoiser path stays a valid implementation: the product configuration and each
+alternative (unfused ResBlocks, fp32 residual stream, stored head output + k_tail, no cluster multicast, epilogue-side
+skip recompute, fully fused ResBlocks) reproduce the golden UnrolledADMMGaussian(4) output of the real reference within
+the BASELINE tolerance.  The switches are read once per process, so each variant runs in a subprocess."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = r'''
+import json, os, sys
+ROOT = sys.argv[1]
+sys.path[:0] = [os.path.join(ROOT, 'galaxy-deconv_b200'), ROOT, os.path.join(ROOT, 'tests')]
+import torch
+import oracle.ref_models as O
+from conftest import rel_l2
+from gdeconv.synth import make_batch
+from models.unrolled_admm_gaussian import UnrolledADMMGaussian
+dev = torch.device('cuda:0')
+g = torch.load(os.path.join(ROOT, 'tests', 'golden', 'golden_v1.pt'))
+i = g['inputs']
+sd = O.seeded_state_dict(lambda: O.UnrolledADMMGaussian(4), g['seeds']['G4'])
+m = UnrolledADMMGaussian(4).eval()
+m.load_state_dict(sd)
+m = m.to(dev)
+out = m(i['y'].to(dev), i['psf'].to(dev), i['alpha'].to(dev)).cpu()
+err_golden = float(rel_l2(out, g['out']['G4']).max())
+# a larger ragged batch (several work items per CTA, partial last item, cluster dummies) against the oracle on a sample
+b = make_batch(7, 301, 100.0, device=dev)
+big = m(b['obs'], b['psf'], b['alpha'])
+idx = torch.tensor([0, 150, 299, 300])
+ref = O.UnrolledADMMGaussian(4).eval(); ref.load_state_dict(sd)
+with torch.no_grad():
+    want = ref(b['obs'][idx].cpu(), b['psf'][idx].cpu(), b['alpha'][idx].cpu())
+err_big = float(rel_l2(big[idx].cpu(), want).max())
+print(json.dumps({'golden': err_golden, 'big': err_big, 'finite': bool(torch.isfinite(big).all())}))
+'''
+
+VARIANTS = [
+    {},
+    {'GDECONV_FUSE_RB': '0'},
+    {'GDECONV_FUSE_RB': '2'},
+    {'GDECONV_HILO': '0'},
+    {'GDECONV_FUSE_HT': '0'},
+    {'GDECONV_TAILG': '0'},
+    {'GDECONV_CLUSTER': '1'},
+    {'GDECONV_CLUSTER': '2'},
+    {'GDECONV_FUSE_RB': '0', 'GDECONV_HILO': '0', 'GDECONV_FUSE_HT': '0', 'GDECONV_CLUSTER': '1'},
+]
+
+
+@pytest.mark.parametrize('env', VARIANTS, ids=lambda e: ','.join(f'{k[8:]}={v}' for k, v in e.items()) or 'default')
+def test_switch_variant_matches_reference(env):
+    r = subprocess.run([sys.executable, '-c', CHILD, ROOT], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res['finite']
+    assert res['golden'] < 1e-3, res          # BASELINE tolerance: relative L2 per stamp
+    assert res['big'] < 1e-3, res
