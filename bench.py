@@ -11,7 +11,7 @@ their NCCL all-gather.  Weak scaling: every rank processes its own `stamps` gala
 
 Printed JSON (rank 0, one line): `value` = whole-job galaxies/s with inputs resident in HBM; `e2e` = the same call with
 pinned HOST inputs (H2D of obs/psf/alpha and D2H of the deconvolved stamps + ellipticities inside the timed region);
-`roofline` = the dominant kernel (k_conv_umma, tcgen05 tap-GEMM) timed live per launch with CUDA events, algorithmic
+`roofline` = the dominant kernel (k_conv_umma and its fused-ResBlock sibling k_rb_umma, tcgen05 tap-GEMM) timed live per launch with CUDA events, algorithmic
 FLOPs / time against the measured bf16 peak of MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle (bit-exact port of
 the reference's torch code) timed on this box's host cores on a bounded sample.
 
@@ -217,7 +217,7 @@ def main():
     clocks = clk.summary()
     ms_e2e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
 
-    # dominant kernel, live: every k_conv_umma launch of one more step bracketed by CUDA events on its stream
+    # dominant kernel, live: every k_conv_umma / k_rb_umma launch of one more step bracketed by CUDA events on its stream
     roof = None
     P = peaks()
     if precision == 'fp16_umma':
@@ -233,12 +233,12 @@ def main():
                 tj = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic_r01.json')))
                 per_chunk = engine._chunk_for(hi - lo)
                 traffic = tj['avg_traffic_bytes_per_launch'] * min(per_chunk, hi - lo) / tj['stamps_per_launch']
-                traffic_note = 'ncu dram__bytes_read+write per k_conv_umma launch (profiles/roofline_traffic_r01.json), scaled by stamps per launch'
+                traffic_note = 'ncu dram__bytes_read+write per tcgen05 conv launch (profiles/roofline_traffic_r01.json), scaled by stamps per launch'
             except Exception:
                 pass
             roof = dict(bound='tensor', achieved=ach, peak=P['tensor_sustained'], unit='TFLOP/s', frac=ach / P['tensor_sustained'], traffic=traffic,
                         traffic_note=traffic_note,
-                        kernel='k_conv_umma', launches_per_step=int(n_k.value), avg_launch_us=ms_k.value * 1e3 / max(1, n_k.value),
+                        kernel='k_conv_umma + k_rb_umma (tcgen05 tap-GEMM convolutions)', launches_per_step=int(n_k.value), avg_launch_us=ms_k.value * 1e3 / max(1, n_k.value),
                         kernel_share_of_step=ms_k.value / ms_step, flops_per_launch_avg=fl_k.value / max(1, n_k.value),
                         peak_source=P['source'] + ', sustained bf16 (kernel timed inside a long step); burst = %.1f' % P['tensor_burst'])
 

@@ -484,7 +484,7 @@ int conv_umma_init() {
     if (const char* e = getenv("GDECONV_ABL")) g_abl = atoi(e);
     if (const char* e = getenv("GDECONV_JCOLS")) { g_jcols = atoi(e) == 256 ? 256 : 128; }
     if (const char* e = getenv("GDECONV_JCOLS1")) { g_jcols1 = atoi(e) == 256 ? 256 : 128; }
-    if (const char* e = getenv("GDECONV_CLUSTER")) { g_cluster = atoi(e); if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4 && g_cluster != 8) g_cluster = 4; }
+    if (const char* e = getenv("GDECONV_CLUSTER")) { g_cluster = atoi(e); if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4) g_cluster = 4; }
     if (const char* e = getenv("GDECONV_ASTAGES")) { g_astages = atoi(e); if (g_astages < 2 || g_astages > MAX_A_STAGES) g_astages = 4; }
     if (const char* e = getenv("GDECONV_BSTAGES")) { g_bstages = atoi(e); if (g_bstages < 2 || g_bstages > MAX_B_STAGES) g_bstages = 6; }
 #define GD_UMMA_ATTR(J, KK)                                                                                                        \

@@ -11,6 +11,6 @@ timeout 1500 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_
 timeout 600 python tools/parity_report.py 48 > gpurun_out/parity.md 2> gpurun_out/parity.err; echo "parity rc=$?"
 BCMD="python bench.py --steps 1 --warmup 3 --stamps 5000 --no-cpu-baseline"
 timeout 600 $BCMD > gpurun_out/plain.log 2>&1 && \
-timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s 185 -c 60 --csv --log-file gpurun_out/launches.csv $BCMD > gpurun_out/ncu1.log 2>&1; echo "ncu list rc=$?"
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s 1115 -c 600 --csv --log-file gpurun_out/launches.csv $BCMD > gpurun_out/ncu1.log 2>&1; echo "ncu list rc=$?"
 timeout 600 $BCMD > gpurun_out/plain2.log 2>&1 && \
-timeout 1200 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,lts__throughput.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:"k_conv_umma|k_head|k_tail|k_g_xupdate|k_subnet|k_g_prologue|k_moments" -s 185 -c 40 --csv --log-file gpurun_out/layers.csv $BCMD > gpurun_out/ncu2.log 2>&1; echo "ncu layers rc=$?"
+timeout 1200 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,lts__throughput.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:"k_conv_umma|k_rb_umma|k_head|k_tail|k_g_xupdate|k_subnet|k_g_prologue|k_moments" -s 185 -c 40 --csv --log-file gpurun_out/layers.csv $BCMD > gpurun_out/ncu2.log 2>&1; echo "ncu layers rc=$?"
