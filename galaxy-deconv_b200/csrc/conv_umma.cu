@@ -45,6 +45,7 @@ struct UmmaCfg {
     int nsl_log2, nb32_log2;   // log2(nslices), log2(ncta / 32): both are powers of two
     int abl;         // diagnostic ablation bits (GDECONV_ABL): 1 = no weight streaming, 2 = no epilogue global traffic, 4 = no activation loads
     int l2pf;        // producer prefetches the residual / skip rows of each item into L2
+    int late_pf;     // epilogue: all residual loads of the next item are issued after this item's last register use
     int cls;         // CTAs per cluster sharing every streamed weight stage by multicast (1 = no cluster)
     int aux_off;     // mode 1: byte offset of the 8 warp-private 4 KB transpose stages of epi_up_unit in dynamic shared memory
     size_t smem;
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                                 }
                             }
                         }
-                        if (nitem < total_items) issue_res(nitem, i);          // registers of unit i are free again
+                        if (!c.late_pf && nitem < total_items) issue_res(nitem, i);          // registers of unit i are free again
                         if constexpr (EPI == EPI_FULL) {
                             if (p.mode == 1) {                   // transposed conv: lane-paired pixel-shuffle stores
                                 epi_up_unit(p, rc.valid, rc.frow0, n0, v, reinterpret_cast<float4*>(smem + c.aux_off) + e * 256);
@@ -414,6 +415,13 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty(acs));
                 if (++acs == 2) { acs = 0; accph ^= 1; }
+                // A warp has six load scoreboards: a prefetch issued between two units makes the second unit's first use of ITS
+                // (long landed) registers wait for the new loads too.  So the next item's loads go out together, here.
+                if (EPI != EPI_PLAIN && c.late_pf && nitem < total_items) {
+#pragma unroll
+                    for (int i = 0; i < UPW_MAX; ++i)
+                        if (i < upw || (nu == 1 && i == 0)) issue_res(nitem, i);
+                }
             }
         }
     }
@@ -428,6 +436,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
 
 static int g_num_sms = 0;
 static int g_cluster = 4;
+static int g_late_pf = -1;     // request the next item's residual after the LAST unit of this item (1) or after each unit (0);
+                               // -1 (default): late for the streamed-weight layers (levels 3-4: 327 -> 297 us, 456 -> 396 us), early for
+                               // the resident ones (level 1 tail conv: 708 vs 794 us), GDECONV_LATEPF overrides
 static int g_jcols = 128;      // accumulator columns per item of the resident-weight 3x3 layers
 static int g_jcols1 = 128;     // ... of the 1-tap (k2s2) layers
 static int g_l2pf = 0;
@@ -482,6 +493,7 @@ int conv_umma_init() {
     GD_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     if (const char* e = getenv("GDECONV_L2PF")) g_l2pf = atoi(e);
     if (const char* e = getenv("GDECONV_ABL")) g_abl = atoi(e);
+    if (const char* e = getenv("GDECONV_LATEPF")) g_late_pf = atoi(e);
     if (const char* e = getenv("GDECONV_JCOLS")) { g_jcols = atoi(e) == 256 ? 256 : 128; }
     if (const char* e = getenv("GDECONV_JCOLS1")) { g_jcols1 = atoi(e) == 256 ? 256 : 128; }
     if (const char* e = getenv("GDECONV_CLUSTER")) { g_cluster = atoi(e); if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4) g_cluster = 4; }
@@ -539,6 +551,7 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     c.l2pf = g_l2pf;
     c.abl = g_abl;
     c.cls = (!c.b_resident && (c.BK / 8) % g_cluster == 0) ? g_cluster : 1;
+    c.late_pf = g_late_pf < 0 ? !c.b_resident : g_late_pf != 0;
     auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
     c.nsl_log2 = ilog2(c.nslices); c.nb32_log2 = ilog2(c.ncta / 32);
     if ((1 << c.nsl_log2) != c.nslices || (1 << c.nb32_log2) != c.ncta / 32) { set_error("conv_umma: N=%d must split into power-of-two slices", p.N); return GD_EUNSUPPORTED; }
