@@ -95,8 +95,8 @@ def _chunk_for(batch, arch=_lib.ARCH_G):
     return min(-(-per // 256) * 256, max(cap, 256))
 
 
-def _workspace(device, arch, prec, chunk):
-    key = (device.index, arch, prec, chunk)
+def _workspace(device, arch, prec, chunk, slot=0):
+    key = (device.index, arch, prec, chunk, slot)
     with _ws_lock:
         hit = _ws_cache.get(key)
         if hit is not None:
@@ -104,10 +104,14 @@ def _workspace(device, arch, prec, chunk):
         nbytes = int(lib.gd_workspace_bytes(arch, prec, chunk))
         if nbytes == 0:
             raise RuntimeError('gd_workspace_bytes rejected the configuration')
-        # at most two workspaces per (device, arch, precision): drop the oldest before allocating a third
-        same = [k for k in _ws_cache if k[:3] == key[:3]]
-        for k in same[:-1] if len(same) >= 2 else []:
-            del _ws_cache[k]
+        # at most two chunk sizes per (device, arch, precision) (each with its stream slots): drop the oldest before a third
+        sizes = []
+        for k in _ws_cache:
+            if k[:3] == key[:3] and k[3] != chunk and k[3] not in sizes:
+                sizes.append(k[3])
+        for old in sizes[:-1] if len(sizes) >= 2 else []:
+            for k in [k for k in _ws_cache if k[:3] == key[:3] and k[3] == old]:
+                del _ws_cache[k]
         buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         check(lib.gd_workspace_init(_ptr(buf), nbytes, arch, prec, chunk, _stream(device)))
         _ws_cache[key] = (buf, nbytes)
@@ -117,6 +121,27 @@ def _workspace(device, arch, prec, chunk):
 def drop_workspaces():
     with _ws_lock:
         _ws_cache.clear()
+
+
+# Chunks of a large batch alternate between the caller's stream and one side stream per device (each with its own
+# workspace): every kernel of the path is a persistent one-CTA-per-SM kernel, so while one chunk's kernel drains its last
+# work items the other chunk's next kernel already fills the freed SMs instead of leaving them idle until the dependent
+# launch starts (GDECONV_STREAMS=1: one stream, chunks back to back inside gd_admm_forward).
+_side_streams = {}
+
+
+def n_streams() -> int:
+    try:
+        return 2 if int(os.environ.get('GDECONV_STREAMS', '2')) >= 2 else 1
+    except ValueError:
+        return 2
+
+
+def _side_stream(device):
+    s = _side_streams.get(device.index)
+    if s is None:
+        s = _side_streams[device.index] = torch.cuda.Stream(device=device)
+    return s
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -193,8 +218,25 @@ class AdmmEngine:
             if want_analysis:
                 shape = (self.n_iters, 3, B, 1, STAMP, STAMP) if self.arch == _lib.ARCH_G else (self.n_iters + 1, 5, B, 1, STAMP, STAMP)
                 ana = torch.empty(shape, device=dev)
-            check(lib.gd_admm_forward(w.handle, llh, int(bool(v0_over_alpha)), _ptr(y), _ptr(psf), _ptr(a), _ptr(out),
-                                      _ptr(rho), _ptr(ana), B, _ptr(ws), nbytes, _stream(dev)))
+            chunk = _chunk_for(B, self.arch)
+            if ana is None and B > chunk and n_streams() == 2:
+                # two chunks in flight: even chunks on the caller's stream, odd chunks on the side stream
+                ws2, _ = _workspace(dev, self.arch, _lib.PRECISIONS[precision], chunk, slot=1)
+                cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                side.wait_stream(cur)
+                for t in (y, psf, a, out, rho):
+                    if t is not None:
+                        t.record_stream(side)
+                for i, c0 in enumerate(range(0, B, chunk)):
+                    nb = min(chunk, B - c0)
+                    st, wsi = (cur, ws) if i % 2 == 0 else (side, ws2)
+                    check(lib.gd_admm_forward(w.handle, llh, int(bool(v0_over_alpha)), _ptr(y[c0:c0 + nb]), _ptr(psf[c0:c0 + nb]),
+                                              _ptr(a[c0:c0 + nb]), _ptr(out[c0:c0 + nb]), _ptr(rho[c0:c0 + nb]) if rho is not None else None,
+                                              None, nb, _ptr(wsi), nbytes, C.c_void_p(st.cuda_stream)))
+                cur.wait_stream(side)
+            else:
+                check(lib.gd_admm_forward(w.handle, llh, int(bool(v0_over_alpha)), _ptr(y), _ptr(psf), _ptr(a), _ptr(out),
+                                          _ptr(rho), _ptr(ana), B, _ptr(ws), nbytes, _stream(dev)))
         return out, rho, ana
 
     def resunet(self, x, precision=None):
