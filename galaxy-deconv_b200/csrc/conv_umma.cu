@@ -45,6 +45,7 @@ struct UmmaCfg {
     int nsl_log2, nb32_log2;   // log2(nslices), log2(ncta / 32): both are powers of two
     int abl;         // diagnostic ablation bits (GDECONV_ABL): 1 = no weight streaming, 2 = no epilogue global traffic, 4 = no activation loads
     int l2pf;        // producer prefetches the residual / skip rows of each item into L2
+    int res_nc;      // hi/lo residual prefetch through ld.global.nc (1) or plain ld.global (0)
     int late_pf;     // epilogue: all residual loads of the next item are issued after this item's last register use
     int cls;         // CTAs per cluster sharing every streamed weight stage by multicast (1 = no cluster)
     int aux_off;     // mode 1: byte offset of the 8 warp-private 4 KB transpose stages of epi_up_unit in dynamic shared memory
@@ -271,7 +272,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                     const uint4* sl = reinterpret_cast<const uint4*>(p.res_lo) + o;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint4 t = __ldg(sh + (size_t)k * Ptot), u = __ldg(sl + (size_t)k * Ptot);
+                        uint4 t, u;
+                        if (c.res_nc) { t = __ldg(sh + (size_t)k * Ptot); u = __ldg(sl + (size_t)k * Ptot); }
+                        else { t = sh[(size_t)k * Ptot]; u = sl[(size_t)k * Ptot]; }
                         d[4 * k] = __uint_as_float(t.x); d[4 * k + 1] = __uint_as_float(t.y); d[4 * k + 2] = __uint_as_float(t.z); d[4 * k + 3] = __uint_as_float(t.w);
                         d[16 + 4 * k] = __uint_as_float(u.x); d[17 + 4 * k] = __uint_as_float(u.y); d[18 + 4 * k] = __uint_as_float(u.z); d[19 + 4 * k] = __uint_as_float(u.w);
                     }
@@ -436,6 +439,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
 
 static int g_num_sms = 0;
 static int g_cluster = 4;
+static int g_res_nc = 1;
 static int g_late_pf = -1;     // request the next item's residual after the LAST unit of this item (1) or after each unit (0);
                                // -1 (default): late for the streamed-weight layers (levels 3-4: 327 -> 297 us, 456 -> 396 us), early for
                                // the resident ones (level 1 tail conv: 708 vs 794 us), GDECONV_LATEPF overrides
@@ -494,6 +498,7 @@ int conv_umma_init() {
     if (const char* e = getenv("GDECONV_L2PF")) g_l2pf = atoi(e);
     if (const char* e = getenv("GDECONV_ABL")) g_abl = atoi(e);
     if (const char* e = getenv("GDECONV_LATEPF")) g_late_pf = atoi(e);
+    if (const char* e = getenv("GDECONV_RESNC")) g_res_nc = atoi(e) != 0;
     if (const char* e = getenv("GDECONV_JCOLS")) { g_jcols = atoi(e) == 256 ? 256 : 128; }
     if (const char* e = getenv("GDECONV_JCOLS1")) { g_jcols1 = atoi(e) == 256 ? 256 : 128; }
     if (const char* e = getenv("GDECONV_CLUSTER")) { g_cluster = atoi(e); if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4) g_cluster = 4; }
@@ -552,6 +557,7 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     c.abl = g_abl;
     c.cls = (!c.b_resident && (c.BK / 8) % g_cluster == 0) ? g_cluster : 1;
     c.late_pf = g_late_pf < 0 ? !c.b_resident : g_late_pf != 0;
+    c.res_nc = g_res_nc;
     auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
     c.nsl_log2 = ilog2(c.nslices); c.nb32_log2 = ilog2(c.ncta / 32);
     if ((1 << c.nsl_log2) != c.nslices || (1 << c.nb32_log2) != c.ncta / 32) { set_error("conv_umma: N=%d must split into power-of-two slices", p.N); return GD_EUNSUPPORTED; }

@@ -37,31 +37,51 @@ __device__ __forceinline__ void zero_fill(float* buf, int n) {
 }
 
 // 3x3 conv + folded BN + ReLU on zero-bordered maps.  in [Cin][H+2][H+2] -> out [Cout][H+2][H+2] (border pre-zeroed).
-// One work item = one pixel x 4 output channels: per (ci, tap) one input LDS, one broadcast LDS.128 of 4 weights, 4 FMAs.
-// wg: [Cin][9][Cout] weights followed by [Cout] biases (pack.cu: api.cu::gd_pack_weights).
+// One work item = 4 adjacent pixels of a row x 4 output channels (16 accumulators): per (ci, tap row) three LDS.64 fetch the
+// 6 inputs the 4 pixels share and three broadcast LDS.128 the weights of the 3 taps -> 48 FMAs per 6 shared-memory loads
+// (the one-pixel version was bound by its 2 loads per 4 FMAs).  Every output still sums bias, then ci-major / tap-minor.
+// wg: [Cin][9][Cout] weights followed by [Cout] biases (pack.cu: api.cu::gd_pack_weights).  H is a multiple of 4.
 __device__ void conv3x3_relu(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ wg,
                              float* wsm, int Cin, int Cout, int H) {
     const int nw = Cout * Cin * 9 + Cout;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) wsm[i] = wg[i];
-    const int Hp = H + 2, HW = H * H, ngrp = Cout >> 2;
+    const int Hp = H + 2, Hq = H >> 2, Q = H * Hq, ngrp = Cout >> 2;
     __syncthreads();
     const float* bias = wsm + Cout * Cin * 9;
-    for (int item = threadIdx.x; item < HW * ngrp; item += blockDim.x) {
-        const int cg = item / HW, p = item - cg * HW, y = p / H, x = p - y * H;
-        float a0 = bias[4 * cg], a1 = bias[4 * cg + 1], a2 = bias[4 * cg + 2], a3 = bias[4 * cg + 3];
-        const float* ip = in + y * Hp + x;                    // top-left tap of pixel (y, x) in the padded map
+    for (int item = threadIdx.x; item < Q * ngrp; item += blockDim.x) {
+        const int cg = item / Q, p = item - cg * Q, y = p / Hq, x0 = (p - y * Hq) << 2;
+        float a[4][4];
+#pragma unroll
+        for (int px = 0; px < 4; ++px) { a[px][0] = bias[4 * cg]; a[px][1] = bias[4 * cg + 1]; a[px][2] = bias[4 * cg + 2]; a[px][3] = bias[4 * cg + 3]; }
+        const float* ip = in + y * Hp + x0;                   // top-left tap of pixel (y, x0) in the padded map (8-byte aligned)
         const float* wp = wsm + 4 * cg;
         for (int ci = 0; ci < Cin; ++ci) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float v = ip[(t / 3) * Hp + (t % 3)];
-                const float4 w = *reinterpret_cast<const float4*>(wp + (ci * 9 + t) * Cout);
-                a0 = fmaf(v, w.x, a0); a1 = fmaf(v, w.y, a1); a2 = fmaf(v, w.z, a2); a3 = fmaf(v, w.w, a3);
+            for (int ky = 0; ky < 3; ++ky) {
+                float v[6];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float2 t = *reinterpret_cast<const float2*>(ip + ky * Hp + 2 * k);
+                    v[2 * k] = t.x; v[2 * k + 1] = t.y;
+                }
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 w = *reinterpret_cast<const float4*>(wp + (ci * 9 + ky * 3 + kx) * Cout);
+#pragma unroll
+                    for (int px = 0; px < 4; ++px) {
+                        a[px][0] = fmaf(v[px + kx], w.x, a[px][0]); a[px][1] = fmaf(v[px + kx], w.y, a[px][1]);
+                        a[px][2] = fmaf(v[px + kx], w.z, a[px][2]); a[px][3] = fmaf(v[px + kx], w.w, a[px][3]);
+                    }
+                }
             }
             ip += Hp * Hp;
         }
-        float* op = out + (4 * cg) * Hp * Hp + (y + 1) * Hp + (x + 1);
-        op[0] = fmaxf(a0, 0.f); op[Hp * Hp] = fmaxf(a1, 0.f); op[2 * Hp * Hp] = fmaxf(a2, 0.f); op[3 * Hp * Hp] = fmaxf(a3, 0.f);
+        float* op = out + (4 * cg) * Hp * Hp + (y + 1) * Hp + (x0 + 1);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+            op[px] = fmaxf(a[px][0], 0.f); op[Hp * Hp + px] = fmaxf(a[px][1], 0.f);
+            op[2 * Hp * Hp + px] = fmaxf(a[px][2], 0.f); op[3 * Hp * Hp + px] = fmaxf(a[px][3], 0.f);
+        }
     }
     __syncthreads();
 }

@@ -1,6 +1,8 @@
 """BASELINE-sized runs checked through size-independent properties (the oracle cannot finish 10,000 stamps of G(8) in
 test time): per-stamp determinism under re-batching, agreement of a random sample with the oracle, and the
 ellipticity tolerance on that sample."""
+import os
+
 import pytest
 import torch
 
@@ -33,3 +35,10 @@ def test_g8_10000_stamps_sampled_against_oracle():
     # a stamp's result does not depend on its neighbours in the batch
     again = m(b['obs'][idx], b['psf'][idx], b['alpha'][idx])
     assert torch.equal(again, out[idx])
+    # ... nor on the two-stream chunk schedule (gdeconv/engine.py): one stream, chunks back to back, gives the same bits
+    os.environ['GDECONV_STREAMS'] = '1'
+    try:
+        single = m(b['obs'], b['psf'], b['alpha'])
+    finally:
+        del os.environ['GDECONV_STREAMS']
+    assert torch.equal(single, out)

@@ -51,6 +51,8 @@ VARIANTS = [
     {'GDECONV_TAILG': '0'},
     {'GDECONV_CLUSTER': '1'},
     {'GDECONV_CLUSTER': '2'},
+    {'GDECONV_LATEPF': '0'},
+    {'GDECONV_LATEPF': '1'},
     {'GDECONV_FUSE_RB': '0', 'GDECONV_HILO': '0', 'GDECONV_FUSE_HT': '0', 'GDECONV_CLUSTER': '1'},
 ]
 
