@@ -28,6 +28,7 @@
 #include "launch.cuh"
 #include "umma_ptx.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace gd {
@@ -43,7 +44,8 @@ constexpr int RB_A_STAGE = RB_WIN * RB_C * 2;     // 39168 B
 constexpr int RB_A_STAGES = 3;
 constexpr int RB_T_BYTES = RB_TROWS * RB_C * 2;   // 32768 B
 constexpr int RB_W_BYTES = 9 * RB_C * RB_C * 2;   // 18432 B
-constexpr int RB_SMEM = RB_A_STAGES * RB_A_STAGE + 2 * RB_T_BYTES + 2 * RB_W_BYTES;   // 219,904 B
+constexpr int RB_I_BYTES = RB_C * RB_C * 2;       // 2048 B: fp16 identity in the B-operand layout (residual-by-MMA)
+constexpr int RB_SMEM = RB_A_STAGES * RB_A_STAGE + 2 * RB_T_BYTES + 2 * RB_W_BYTES + RB_I_BYTES;   // 221,952 B
 
 struct RbHt { float head[9 * RB_C], tail[9 * RB_C]; };
 
@@ -69,7 +71,7 @@ __device__ __forceinline__ void rb_tail(const float* __restrict__ tw, const floa
 
 // p1: first conv (a = x16, w = W1; its out16 is NOT written), p2: second conv with the full epilogue description.
 template <int HT>
-__global__ void __launch_bounds__(UMMA_THREADS, 1) k_rb_umma(const ConvParams p1, const ConvParams p2, const int total_items,
+__global__ void __launch_bounds__(UMMA_THREADS, 1) k_rb_umma(const ConvParams p1, const ConvParams p2, const int total_items, const int res_mma,
                                                              const __grid_constant__ RbHt htw) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[2 * RB_A_STAGES + 1 + 12];
@@ -102,6 +104,15 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_rb_umma(const ConvParams p1
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // identity B operand [K/8][N][8]: element (k, n) = (k == n).  With it the tensor pipe adds the hi half of the residual
+        // (= the ResBlock's own fp16 input, already resident in the x window) to D2: one more "tap", no LSU traffic.
+        __half* I = reinterpret_cast<__half*>(w_smem + 2 * RB_W_BYTES);
+        for (int i = threadIdx.x; i < RB_C * RB_C; i += blockDim.x) {
+            const int kc = i / (RB_C * 8), n = (i / 8) % RB_C, kk = i % 8;
+            I[i] = __float2half(kc * 8 + kk == n ? 1.f : 0.f);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -141,6 +152,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_rb_umma(const ConvParams p1
         const uint64_t t_desc0 = smem_desc(smem_u32(t_smem), RB_TROWS * 16, 128);
         const uint64_t w1_desc0 = smem_desc(smem_u32(w_smem), RB_C * 16, 128);
         const uint64_t w2_desc0 = smem_desc(smem_u32(w_smem) + RB_W_BYTES, RB_C * 16, 128);
+        const uint64_t i_desc0 = smem_desc(smem_u32(w_smem) + 2 * RB_W_BYTES, RB_C * 16, 128);
         constexpr uint32_t A_KK = (2 * RB_WIN * 16) >> 4, T_KK = (2 * RB_TROWS * 16) >> 4, W_KK = (2 * RB_C * 16) >> 4;
         constexpr uint32_t W_TAP = (RB_C / 8) * RB_C;       // 16-byte units per tap of the packed weights
         mbar_wait(w_full, 0);
@@ -163,7 +175,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_rb_umma(const ConvParams p1
                     }
                 }
                 __syncwarp();
-                tc_commit_pred(a_empty(as), leader);
+                if (!res_mma || jw >= RB_J2) tc_commit_pred(a_empty(as), leader);     // res_mma: warps 0-2 release the window after phase 2
                 tc_commit_pred(d1_full(b), leader);
                 if (++as == RB_A_STAGES) { as = 0; aph ^= 1; }
             }
@@ -182,8 +194,15 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_rb_umma(const ConvParams p1
                         if (tap == 0) tc_mma_f16(d, at, bt, idesc, 0u); else tc_mma_f16_acc(d, at, bt, idesc);
                         tc_mma_f16_acc(d, at + T_KK, bt + W_KK, idesc);
                     }
+                    if (res_mma) {                           // D2 += x_hi * I  (output rows of tile jw inside the x window of item i)
+                        const uint32_t as2 = (uint32_t)(i % RB_A_STAGES);
+                        const uint64_t ax = a_desc0 + (uint64_t)(as2 * (RB_A_STAGE >> 4) + (uint32_t)(RB_HALO + RB_LEAD + jw * MTILE));
+                        tc_mma_f16_acc(d, ax, i_desc0, idesc);
+                        tc_mma_f16_acc(d, ax + A_KK, i_desc0 + W_KK, idesc);
+                    }
                 }
                 __syncwarp();
+                if (res_mma) tc_commit_pred(a_empty(i % RB_A_STAGES), leader);
                 tc_commit_pred(t_empty(b2), leader);
                 tc_commit_pred(d2_full(b2), leader);
             }
@@ -240,7 +259,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_rb_umma(const ConvParams p1
                 const uint4* sl = reinterpret_cast<const uint4*>(p2.res_lo) + o;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    const uint4 t = __ldg(sh + (size_t)k * Ptot), u = __ldg(sl + (size_t)k * Ptot);
+                    const uint4 u = __ldg(sl + (size_t)k * Ptot);
+                    const uint4 t = res_mma ? make_uint4(0u, 0u, 0u, 0u) : __ldg(sh + (size_t)k * Ptot);   // res_mma: hi was added by the tensor pipe
                     add[j][4 * k] = __uint_as_float(t.x); add[j][4 * k + 1] = __uint_as_float(t.y); add[j][4 * k + 2] = __uint_as_float(t.z); add[j][4 * k + 3] = __uint_as_float(t.w);
                     add[j][8 + 4 * k] = __uint_as_float(u.x); add[j][9 + 4 * k] = __uint_as_float(u.y); add[j][10 + 4 * k] = __uint_as_float(u.z); add[j][11 + 4 * k] = __uint_as_float(u.w);
                 }
@@ -368,14 +388,18 @@ int launch_conv_rb(const ConvParams& p1, const ConvParams& p2, cudaStream_t st) 
     cudaEvent_t e1 = nullptr;
     const double flops = 2.0 * 2.0 * (double)(p2.g.M / p2.g.S) * p2.g.H * p2.g.W * (double)RB_C * RB_C * 9;   // both convs, valid pixels
     { int rc = conv_profile_mark(flops, st, &e1); if (rc != GD_OK) return rc; }
+    // residual-by-MMA: the hi half of an hi/lo residual that IS this ResBlock's fp16 input is added by an identity "tap"
+    static int res_mma_env = -1;
+    if (res_mma_env < 0) { const char* e = getenv("GDECONV_RESMMA"); res_mma_env = e ? atoi(e) != 0 : 0; }   // off until validated on the GPU
+    const int res_mma = res_mma_env && p2.res_hi && p2.res_hi == p1.a;
     RbHt hw;
     memset(&hw, 0, sizeof(hw));
     if (p2.head_t || p2.tail_part) {
         if (p2.head_t) memcpy(hw.head, p2.head_w, sizeof(hw.head));
         if (p2.tail_part) memcpy(hw.tail, p2.tail_w, sizeof(hw.tail));
-        k_rb_umma<1><<<grid, UMMA_THREADS, RB_SMEM, st>>>(p1, p2, items, hw);
+        k_rb_umma<1><<<grid, UMMA_THREADS, RB_SMEM, st>>>(p1, p2, items, res_mma, hw);
     } else {
-        k_rb_umma<0><<<grid, UMMA_THREADS, RB_SMEM, st>>>(p1, p2, items, hw);
+        k_rb_umma<0><<<grid, UMMA_THREADS, RB_SMEM, st>>>(p1, p2, items, res_mma, hw);
     }
     GD_LAUNCHED();
     if (e1) GD_CUDA_CHECK(cudaEventRecord(e1, st));
