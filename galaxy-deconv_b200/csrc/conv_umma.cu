@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -594,16 +595,22 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t st) {
         at[0].val.clusterDim.x = (unsigned)c.cls; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         static std::map<std::pair<const void*, int>, int> max_clusters;      // per (kernel, cluster size)
-        auto key = std::make_pair((const void*)kern, c.cls);
-        auto it = max_clusters.find(key);
-        if (it == max_clusters.end()) {
-            int n = 0;
-            cfg.gridDim = dim3((unsigned)(g_num_sms / c.cls * c.cls));
-            GD_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-            if (n < 1) { set_error("conv_umma: no cluster of %d CTAs fits", c.cls); return GD_ECUDA; }
-            it = max_clusters.emplace(key, n).first;
+        static std::mutex mu;
+        int max_cl;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto key = std::make_pair((const void*)kern, c.cls);
+            auto it = max_clusters.find(key);
+            if (it == max_clusters.end()) {
+                int n = 0;
+                cfg.gridDim = dim3((unsigned)(g_num_sms / c.cls * c.cls));
+                GD_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+                if (n < 1) { set_error("conv_umma: no cluster of %d CTAs fits", c.cls); return GD_ECUDA; }
+                it = max_clusters.emplace(key, n).first;
+            }
+            max_cl = it->second;
         }
-        const int clusters = iters < it->second ? iters : it->second;
+        const int clusters = iters < max_cl ? iters : max_cl;
         cfg.gridDim = dim3((unsigned)(clusters * c.cls));
         GD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p, c, hw));
         return GD_OK;
