@@ -496,8 +496,22 @@ static int subchunk_size() {
     return g_subchunk;
 }
 
+// m_head fused into k_g_xupdate (path G, tcgen05, C0 = 32, head/tail fusion); GDECONV_XHEAD=0: separate k_head32 launch
+static int g_xhead = -1;
+static int xhead_mode() {
+    if (g_xhead < 0) {
+        const char* e = getenv("GDECONV_XHEAD");
+        g_xhead = e ? atoi(e) : 1;
+    }
+    return g_xhead;
+}
+static int g_fuse_ht_fwd();
+static bool xhead_applies(const GdWeights* W) {
+    return xhead_mode() && W->precision == PREC_FP16_UMMA && W->nc[0] == 32 && g_fuse_ht_fwd();
+}
+
 static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const float* tscale, float* zout, int nb,
-                         cudaStream_t st) {
+                         cudaStream_t st, bool head_done = false) {
     const int prec = W->precision;
     const Geom* g = ws.g;
     const int* C = ws.C;
@@ -511,7 +525,8 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
     {   // head (ResUNet.py:31): x1 = conv(t)  -> skip32[0] (fp32) + a16[0]
         ConvParams p = conv_base(g[0], nb);
         p.N = C[0]; p.out32 = fuse ? nullptr : ws.skip32[0]; p.out16 = ws.a16[0];
-        GD_TRY(launch_head(t, W->head, C[0] <= 64 ? W->head_h : nullptr, C[0], p, nb, prec, fuse ? ws.tpad : nullptr, st));
+        if (!(head_done && fuse))
+            GD_TRY(launch_head(t, W->head, C[0] <= 64 ? W->head_h : nullptr, C[0], p, nb, prec, fuse ? ws.tpad : nullptr, st));
     }
     auto at4 = [&](float* base, int s0) -> float* { return base + (size_t)s0 * g[0].S; };    // 4-byte rows of level 0
     // one ResBlock (resnet_basicblock.py:69-71) on stamps [s0, s0+n): stream + conv(relu(conv(stream))) -> two layers
@@ -623,6 +638,8 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
     return launch_tail(ws.p32a[0], W->tail, C[0], g[0], tscale, zout, nb, st);
 }
 
+static int g_fuse_ht_fwd() { return !chain_mode() && fuse_ht_mode(); }
+
 static int rho_chunk(const GdWeights* W, const Ws& ws, const float* psf, const float* alpha, int nb, cudaStream_t st) {
     if (W->has_subnet) return launch_subnet(W->sub, psf, alpha, ws.rho, nb, st);
     if (W->has_rho_param) return launch_fill_rho(W->rho_param, W->n_rho, ws.rho, nb, st);
@@ -701,9 +718,11 @@ extern "C" int gd_admm_forward(const GdWeights* W, int llh, int u_v0_over_alpha,
             GD_TRY(launch_g_prologue(yc, kc, ac, ws.spec, ws.HtH, ws.z, ws.u, ws.x, nb, st));
             if (n == 0) GD_TRY(copy_f32(out + o, ws.z, ni, st));
             for (int it = 0; it < n; ++it) {
-                GD_TRY(launch_g_xupdate(ws.spec, ws.HtH, ws.rho, nr, it, ws.z, ws.x, ws.u, ws.t, ws.tscale, nb, st));
+                const bool xh = xhead_applies(W);
+                if (xh) GD_TRY(launch_g_xupdate(ws.spec, ws.HtH, ws.rho, nr, it, ws.z, ws.x, ws.u, ws.t, ws.tscale, nb, st, W->head_h, &ws.g[0], ws.a16[0], ws.tpad));
+                else GD_TRY(launch_g_xupdate(ws.spec, ws.HtH, ws.rho, nr, it, ws.z, ws.x, ws.u, ws.t, ws.tscale, nb, st));
                 float* zdst = it == n - 1 ? out + o : ws.z;
-                GD_TRY(resunet_chunk(W, ws, ws.t, ws.tscale, zdst, nb, st));
+                GD_TRY(resunet_chunk(W, ws, ws.t, ws.tscale, zdst, nb, st, xh));
                 if (analysis) {
                     float* A = analysis + (size_t)it * 3 * plane + o;
                     GD_TRY(copy_f32(A, ws.x, ni, st));

@@ -113,7 +113,6 @@ __global__ void __launch_bounds__(128) k_head(const float* __restrict__ t, const
 // Product-path head for C0 = 32 (tcgen05 path with head/tail fusion): only the fp16 operand copy and the padded-linear copy
 // of the input are written (the fp32 head output is recomputed where it is consumed).  The 288 weights are kernel
 // parameters, i.e. immediate constant-bank operands of the FFMAs -- the generic k_head is bound by its shared-memory loads.
-struct HeadW32 { float w[9 * 32]; };
 __global__ void __launch_bounds__(128) k_head32(const float* __restrict__ t, const __grid_constant__ HeadW32 hw, Geom g, __half* __restrict__ out16,
                                                 float* __restrict__ tpad, int batch) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;

@@ -112,6 +112,9 @@ struct ConvParams {
     const float* tail_w;      // [9][N] fp32, HOST pointer
 };
 
+// fp32 m_head weights [tap][32] passed as a kernel parameter (immediate constant-bank FFMA operands): k_head32, k_g_xupdate
+struct HeadW32 { float w[9 * 32]; };
+
 // ---------------------------------------------------------------------------------------------------
 // error plumbing (C ABI returns ints; message retrievable through gd_last_error())
 // ---------------------------------------------------------------------------------------------------

@@ -22,7 +22,8 @@ int launch_conv_rb(const ConvParams& p1, const ConvParams& p2, cudaStream_t st);
 int launch_g_prologue(const float* y, const float* psf, const float* alpha, float2* Pc, float* HtH, float* z, float* u,
                       float* x, int batch, cudaStream_t st);
 int launch_g_xupdate(const float2* Pc, const float* HtH, const float* rho, int n_rho, int it, const float* z, float* x,
-                     float* u, float* t, float* tscale, int batch, cudaStream_t st);
+                     float* u, float* t, float* tscale, int batch, cudaStream_t st, const float* head_w_host = nullptr,
+                     const Geom* g0 = nullptr, void* a16 = nullptr, float* tpad = nullptr);
 int launch_g_dual_out(const float* rho, int n_rho, int it, const float* x, const float* z, const float* u, float* uo,
                       int batch, cudaStream_t st);
 int launch_scale_in(const float* in, float* t, float* tscale, int batch, cudaStream_t st);

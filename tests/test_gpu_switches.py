@@ -52,6 +52,8 @@ VARIANTS = [
     {'GDECONV_CLUSTER': '1'},
     {'GDECONV_CLUSTER': '2'},
     {'GDECONV_LATEPF': '0'},
+    {'GDECONV_XHEAD': '0'},
+    {'GDECONV_RESMMA': '1'},
     {'GDECONV_LATEPF': '1'},
     {'GDECONV_FUSE_RB': '0', 'GDECONV_HILO': '0', 'GDECONV_FUSE_HT': '0', 'GDECONV_CLUSTER': '1'},
 ]
