@@ -63,3 +63,26 @@ def test_hilo_split_carries_22_bits():
     lo = (x - hi.float()).half()
     err = (x.double() - (hi.double() + lo.double())).abs() / x.double().abs()
     assert err.max() < 2.0 ** -21
+
+
+def test_transposed_conv_column_order_is_a_bijection_with_paired_subpixels():
+    """Column order of the packed k2s2 transposed-conv weights on the tcgen05 path (api.cu pack_up, conv_epilogue.cuh
+    epi_up_unit): n = dy*2Cf + (c/16)*32 + ((c%16)/4)*8 + dx*4 + c%4.  Every 32-column accumulator unit must hold ONE dy,
+    16 consecutive channels and BOTH sub-pixels dx, in the piece order (g = (c%16)/4, dx) the epilogue's 16-byte pieces use."""
+    for Cf in (32, 64, 128, 256):
+        seen = {}
+        for dy in range(2):
+            for dx in range(2):
+                for c in range(Cf):
+                    n = dy * 2 * Cf + (c // 16) * 32 + ((c % 16) // 4) * 8 + dx * 4 + c % 4
+                    assert n not in seen
+                    seen[n] = (dy, dx, c)
+        assert sorted(seen) == list(range(4 * Cf))
+        for u in range(4 * Cf // 32):
+            cols = [seen[32 * u + j] for j in range(32)]
+            assert len({d for d, _, _ in cols}) == 1                       # one fine row parity per unit
+            assert u // (2 * Cf // 32) == cols[0][0]                       # dy = n0 >> (log2(Cf) + 1)
+            c0 = ((32 * u) % (2 * Cf)) // 32 * 16                          # c0 = ((n0 & (2Cf-1)) >> 5) * 16
+            for j, (dy, dx, c) in enumerate(cols):
+                g, dxj, e = j // 8, (j // 4) % 2, j % 4
+                assert (dx, c) == (dxj, c0 + 4 * g + e)
