@@ -49,5 +49,6 @@ def test_library_is_sm100a_native():
         pytest.skip('cuobjdump not available')
     sass = subprocess.run([cuobjdump, '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert 'sm_100a' in sass
-    for mnemonic in ('UTCHMMA', 'LDTM', 'UBLKCP'):
+    # tcgen05.mma, TMEM loads, bulk-async copies; cluster-multicast weight stages + multicast tcgen05.commit + cluster barrier
+    for mnemonic in ('UTCHMMA', 'LDTM', 'UBLKCP', 'UBLKCP.S.G.MULTICAST', 'UTCBAR.MULTICAST', 'UCGABAR_ARV'):
         assert mnemonic in sass, mnemonic
