@@ -182,6 +182,7 @@ static int init_once(int device) {
     GD_TRY(conv_umma_init());
     GD_TRY(conv_chain_init());
     GD_TRY(conv_rb_init());
+    GD_TRY(conv_l1chain_init());
     done.fetch_or(1u << device);
     return GD_OK;
 }
@@ -505,9 +506,23 @@ static int xhead_mode() {
     }
     return g_xhead;
 }
+// Level-0 chain kernels (conv_l1chain.cu): m_head + the two ResBlocks of m_down1, and the two ResBlocks of m_up1 + the m_tail partial
+// sums, each as ONE launch with the intermediates in shared / tensor memory.  GDECONV_L1CHAIN=0 restores one launch per layer pair.
+static int g_l1chain = -1;
+static int l1chain_mode() {
+    if (g_l1chain < 0) {
+        const char* e = getenv("GDECONV_L1CHAIN");
+        g_l1chain = e ? atoi(e) : 1;
+    }
+    return g_l1chain;
+}
 static int g_fuse_ht_fwd();
+static bool l1chain_applies(const GdWeights* W) {
+    return l1chain_mode() && W->precision == PREC_FP16_UMMA && W->nc[0] == 32 && g_fuse_ht_fwd() && hilo_mode() && tail_g_mode() &&
+           subchunk_size() >= (1 << 30);
+}
 static bool xhead_applies(const GdWeights* W) {
-    return xhead_mode() && W->precision == PREC_FP16_UMMA && W->nc[0] == 32 && g_fuse_ht_fwd();
+    return xhead_mode() && W->precision == PREC_FP16_UMMA && W->nc[0] == 32 && g_fuse_ht_fwd() && !l1chain_applies(W);
 }
 
 static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const float* tscale, float* zout, int nb,
@@ -522,7 +537,8 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
     // tcgen05 path: x1 is never stored in fp32; its consumers recompute it from tpad (ConvParams::head_t)
     const bool fuse = prec == PREC_FP16_UMMA && !chain_mode() && fuse_ht_mode() && C[0] <= 64;
     const bool hilo = prec == PREC_FP16_UMMA && !chain_mode() && hilo_mode();
-    {   // head (ResUNet.py:31): x1 = conv(t)  -> skip32[0] (fp32) + a16[0]
+    const bool l1chain = l1chain_applies(W);      // level 0 runs in the two chain kernels: no separate head launch, no level-0 fp32 buffers
+    if (!l1chain) {   // head (ResUNet.py:31): x1 = conv(t)  -> skip32[0] (fp32) + a16[0]
         ConvParams p = conv_base(g[0], nb);
         p.N = C[0]; p.out32 = fuse ? nullptr : ws.skip32[0]; p.out16 = ws.a16[0];
         if (!(head_done && fuse))
@@ -597,6 +613,10 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         return resblock(L, s0, n, wb, res_b, skip_b, out32_b, out16_b, s2d_b);
     };
     auto down_stage = [&](int L, int s0, int n) -> int {          // m_down{L+1} (ResUNet.py:32-34)
+        if (L == 0 && l1chain) {
+            const void* w4[4] = {W->down_rb[0][0][0], W->down_rb[0][0][1], W->down_rb[0][1][0], W->down_rb[0][1][1]};
+            GD_TRY(launch_l1chain_down(g[0], g[1], n, t + (size_t)s0 * NPIX, W->head_h, w4, at(ws.d16[1], 1, s0), st));
+        } else
         GD_TRY(resblock_pair(L, s0, n, W->down_rb[L][0], W->down_rb[L][1], ws.skip32[L], ws.p32a[L], ws.a16[L], ws.p32a[L], nullptr,
                              nullptr, nullptr, ws.d16[L + 1]));
         ConvParams p = conv_base(g[L + 1], n);         // k2s2 strided conv as a 1-tap GEMM on the space-to-depth copy
@@ -611,6 +631,10 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         p.out32 = (float*)at(ws.p32a[L], L, s0); p.out16 = at(ws.a16[L], L, s0);
         if (hilo) { p.out_lo = at(ws.lo16[L], L, s0); p.out32 = nullptr; }
         GD_TRY(run_conv(p, prec, st));
+        if (L == 0 && l1chain) {
+            const void* w4[4] = {W->up_rb[0][0][0], W->up_rb[0][0][1], W->up_rb[0][1][0], W->up_rb[0][1][1]};
+            return launch_l1chain_up(g[0], g[1], n, at(ws.a16[0], 0, s0), at(ws.lo16[0], 0, s0), W->tail_h, w4, at4(ws.tail_part, s0), st);
+        }
         if (L > 0) return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L],
                                         ws.skip32[L], nullptr, ws.a16[L], nullptr);
         return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L], ws.skip32[L],
@@ -633,6 +657,7 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         GD_TRY(up_stage(0, s0, n));
     }
     // tail (ResUNet.py:39): conv(x + x1), times the per-stamp input scale
+    if (l1chain) return launch_tail_gather(ws.tail_part, 1, g[0], tscale, zout, nb, t, W->tail_head_g, st, 1);
     if (fuse) return launch_tail_gather(ws.tail_part, (!chain_mode() && fuse_rb_mode() >= 2 && C[0] == 32) ? 2 : C[0] / 32, g[0], tscale, zout, nb,
                                         ws.tpad, tail_g_mode() ? W->tail_head_g : nullptr, st);
     return launch_tail(ws.p32a[0], W->tail, C[0], g[0], tscale, zout, nb, st);

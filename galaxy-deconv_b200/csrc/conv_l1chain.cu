@@ -1,0 +1,497 @@
+// Level-0 chain kernels of the ResUNet denoiser (32 channels at 48x48, models/ResUNet.py:31-32 and :38-39), tcgen05 path:
+//
+//   DOWN:  x1 = m_head(t);  x = ResBlock(ResBlock(x1))                  -> space-to-depth copy for the m_down1 strided conv
+//   UP:    x  = ResBlock(ResBlock(convT output, hi/lo from HBM))        -> per-tap m_tail partial sums (k_tail_gather)
+//
+// i.e. FOUR 3x3 convolutions (two `x + conv(ReLU(conv(x)))` blocks, models/resnet_basicblock.py:69-71) per launch with every
+// intermediate on chip.  Why: at this level one conv per launch is HBM-bound (768 MB per 32-channel fp16 map of 5000 stamps) and
+// even the fused ResBlock kernel (conv_rb.cu) moves 3.1 GB per block for 0.3 ms of tensor work.  Here a work item is HALF A
+// STAMP (24 output rows + the 4 rows of halo the four convs need = a 28-row window, 1372 rows of the padded-linear layout):
+//   * the fp16 operand copies of the stream (X) and of ReLU(conv1) (T) live in shared memory, two buffers of 4 chunk planes
+//     x 1428 rows x 16 B; planes are separated by 56 zero rows that are never written, which serve as the zero row above /
+//     below the stamp and absorb the tap shifts of the first / last tile;
+//   * the fp32 residual stream lives in TENSOR MEMORY (10 tiles x 32 columns): the second conv of a block adds its
+//     accumulator to it in the epilogue (tcgen05.ld + tcgen05.st), nothing is rounded to fp16 on the residual path;
+//   * conv accumulators: 2 stages x 3 tiles x 32 TMEM columns: a unit of 3 tiles is issued tap by tap (three independent
+//     accumulator chains keep the tensor pipe full) and its epilogue overlaps the MMAs of the next unit;
+//   * weights (18 KB per conv) stream through two shared-memory slots, one layer ahead.
+// The halo is RECOMPUTED (layer l of a top item is valid on rows y < 27 - l, mirrored for bottom items): 41 tiles of MMA work per
+// item for 36.75 tiles of output, no inter-CTA exchange.  Tiles are 128 consecutive padded-linear rows; a tile of layer l+1
+// is issued as soon as the epilogues of the layer-l tiles under its 3x3 footprint have arrived (per-tile mbarriers), so the
+// tensor pipe never drains at a layer boundary.
+//
+// Warp roles (448 threads, one persistent CTA per SM):
+//   warp 0      producer: weight slots; UP: the item's hi -> X and lo -> T windows; DOWN: 29 rows of t (bulk async copies)
+//   warp 1      TMEM allocator + MMA issuer (one elected lane, straight-line 54 MMAs per 3-tile unit)
+//   warps 2-5   helpers (one per TMEM lane quarter): DOWN: x1 = m_head(t) in fp32 on CUDA cores -> X (fp16) + stream (TMEM);
+//               UP: stream = hi + lo
+//   warps 6-13  epilogue: two groups of four (one warp per lane quarter), alternating units
+#include "conv_epilogue.cuh"
+#include "kernels.cuh"
+#include "launch.cuh"
+#include "umma_ptx.cuh"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace gd {
+
+constexpr int LC_C = 32;
+constexpr int LC_WP = 49;                            // padded row length at 48x48
+constexpr int LC_WIN_Y = 28;                         // image rows per item window
+constexpr int LC_ROWS = LC_WIN_Y * LC_WP;            // 1372
+constexpr int LC_GAP = 56;                           // zero rows between planes (>= Wp + 1)
+constexpr int LC_PSTRIDE = LC_ROWS + LC_GAP;         // 1428
+constexpr int LC_ACT_BYTES = (8 * LC_PSTRIDE + LC_GAP) * 16;    // 183,680: planes 0-3 = X, 4-7 = T
+constexpr int LC_W_BYTES = 9 * LC_C * LC_C * 2;      // 18,432
+constexpr int LC_TWIN_ROWS = 29;                     // image rows of the 1-channel input a DOWN item needs (window + 1 row of halo, clipped)
+constexpr int LC_TWIN_BYTES = LC_TWIN_ROWS * STAMP * 4;          // 5,568
+constexpr int LC_SMEM = LC_ACT_BYTES + 2 * LC_W_BYTES + 5632;   // 226,176
+constexpr int LC_BOT_Y0 = 20;                        // first image row of a bottom item's window
+constexpr int LC_BOT = LC_ROWS - 10 * MTILE;         // 92: first row of the 10-tile grid of a bottom item
+constexpr int LC_OWN = 24 * LC_WP;                   // 1176 rows of final output per item
+constexpr int LC_THREADS = 14 * 32;
+constexpr int LC_STREAM_TILES = 10;
+constexpr int LC_J = 3;                              // tiles per MMA unit: their MMAs are interleaved tap by tap (independent accumulator chains)
+constexpr int LC_ACC_COL = LC_STREAM_TILES * LC_C;   // 320: two accumulator stages of LC_J x 32 columns follow the stream (512 in all)
+constexpr int LC_HEAD_TILES = 11;
+
+enum { LCB_W_FULL = 0, LCB_W_EMPTY = 2, LCB_ACC_FULL = 4, LCB_ACC_EMPTY = 6, LCB_X_FULL = 8, LCB_T_FULL = 9, LCB_X_FREE = 10,
+       LCB_T_FREE = 11, LCB_ITEM_DONE = 12, LCB_X_READY = 13, LCB_TILE_DONE = LCB_X_READY + LC_HEAD_TILES, LCB_S_READY = LCB_TILE_DONE + 3 * 11,
+       LCB_TWIN_FULL = LCB_S_READY + LC_STREAM_TILES, LCB_TWIN_EMPTY, LCB_COUNT };
+
+struct L1ChainParams {
+    int nb;                        // stamps
+    Geom g0, g1;                   // level 0 (48x48) and level 1 (24x24) geometry of the chunk
+    const float* t;                // DOWN: scaled denoiser input [nb][48*48]
+    const void *x_hi, *x_lo;       // UP: fp16 hi/lo planes of the m_up1 transposed-conv output [4][g0.Ptot][8]
+    const void* w[4];              // packed 3x3 weights [tap][4][32][8]: block 1 conv 1, conv 2, block 2 conv 1, conv 2
+    void* s2d;                     // DOWN: space-to-depth copy [16][g1.Ptot][8] for the strided conv
+    float* tail_part;              // UP: [9][g0.Ptot] per-tap m_tail partial sums
+};
+struct L1ChainHT { float head[9 * LC_C], tail[9 * LC_C]; };
+
+__device__ __forceinline__ int lc_ntiles(int L) { return L == 0 ? 11 : 10; }
+// tile i of layer L (0..3) of a top (h = 0) / bottom (h = 1) item: first row r and the rows [wlo, whi) its epilogue writes
+__device__ __forceinline__ void lc_tile(int L, int h, int i, int& r, int& wlo, int& whi) {
+    if (h == 0) {
+        if (L == 0 && i == 10) { r = 27 * LC_WP - MTILE; wlo = 10 * MTILE; whi = 27 * LC_WP; }      // overlaps tile 9: writes only the new rows
+        else { r = MTILE * i; wlo = r; whi = r + MTILE; }
+    } else {
+        if (L == 0) {
+            if (i == 0) { r = LC_WP; wlo = LC_WP; whi = LC_BOT; }
+            else { r = LC_BOT + MTILE * (i - 1); wlo = r; whi = r + MTILE; }
+        } else { r = LC_BOT + MTILE * i; wlo = r; whi = r + MTILE; }
+    }
+}
+__device__ __forceinline__ int lc_tile_start(int L, int h, int i) { int r, a, b; lc_tile(L, h, i, r, a, b); return r; }
+__device__ __forceinline__ int lc_stream_start(int h, int i) { return (h ? LC_BOT : 0) + MTILE * i; }
+__device__ __forceinline__ int lc_head_start(int h, int j) { return (h ? LC_BOT - MTILE : 0) + MTILE * j; }
+
+// 9 per-tap partial sums of m_tail over the 32 channels of one row (weights = constant-bank operands)
+__device__ __forceinline__ void lc_tail(const float* __restrict__ tw, const float* v, float* dst, size_t Ptot) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s[k & 3] = fmaf(v[k], tw[t * LC_C + k], s[k & 3]);
+        dst[(size_t)t * Ptot] = (s[0] + s[1]) + (s[2] + s[3]);
+    }
+}
+
+template <int MODE>      // 0 = DOWN, 1 = UP
+__global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams p, const __grid_constant__ L1ChainHT htw) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[LCB_COUNT];
+    __shared__ uint32_t tmem_slot;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    unsigned char* w_smem = smem + LC_ACT_BYTES;
+    const float* twin = reinterpret_cast<const float*>(smem + LC_ACT_BYTES + 2 * LC_W_BYTES);   // DOWN: rows [ylo, ylo + 29) of the item's stamp of t
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(LCB_W_FULL + s), 1); mbar_init(bar(LCB_W_EMPTY + s), 1);
+            mbar_init(bar(LCB_ACC_FULL + s), 1); mbar_init(bar(LCB_ACC_EMPTY + s), 4);
+        }
+        mbar_init(bar(LCB_X_FULL), 1); mbar_init(bar(LCB_T_FULL), 1); mbar_init(bar(LCB_X_FREE), 1); mbar_init(bar(LCB_T_FREE), 1);
+        mbar_init(bar(LCB_ITEM_DONE), 8);
+        for (int j = 0; j < LC_HEAD_TILES; ++j) mbar_init(bar(LCB_X_READY + j), 4);
+        for (int j = 0; j < 33; ++j) mbar_init(bar(LCB_TILE_DONE + j), 4);
+        for (int j = 0; j < LC_STREAM_TILES; ++j) mbar_init(bar(LCB_S_READY + j), 4);
+        mbar_init(bar(LCB_TWIN_FULL), 1); mbar_init(bar(LCB_TWIN_EMPTY), 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // zero the activation planes once: the gaps and the pad pixels (x = 48) are never written afterwards
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for (int i = threadIdx.x; i < LC_ACT_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int total_items = 2 * p.nb;
+    const int n_my = total_items > (int)blockIdx.x ? (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t Ptot0 = (uint32_t)p.g0.Ptot;
+    // byte offset of row s of plane pl inside the activation region
+    auto row_off = [](int pl, int s) { return (uint32_t)((pl * LC_PSTRIDE + LC_GAP + s) * 16); };
+
+    if (warp == 0) {
+        // ===== producer =====
+        if (lane == 0) {
+            auto load_w = [&](int k, int L) {
+                const int Lc = 4 * k + L, slot = Lc & 1;
+                mbar_wait(bar(LCB_W_EMPTY + slot), ((Lc >> 1) & 1) ^ 1);
+                mbar_expect_tx(bar(LCB_W_FULL + slot), (uint32_t)LC_W_BYTES);
+                const uint32_t dst = smem_u32(w_smem) + (uint32_t)slot * LC_W_BYTES;
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(p.w[L]);
+                bulk_g2s(dst, src, LC_W_BYTES / 2, bar(LCB_W_FULL + slot));
+                bulk_g2s(dst + LC_W_BYTES / 2, src + LC_W_BYTES / 2, LC_W_BYTES / 2, bar(LCB_W_FULL + slot));
+            };
+            auto load_act = [&](int it, const void* src, int pl0, uint32_t full) {
+                const int b = it >> 1, h = it & 1;
+                const size_t row0 = (size_t)p.g0.base0 + (size_t)b * p.g0.S + (size_t)h * (LC_BOT_Y0 * LC_WP);
+                mbar_expect_tx(full, 4u * LC_ROWS * 16u);
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    bulk_g2s(smem_u32(smem) + row_off(pl0 + ch, 0), reinterpret_cast<const unsigned char*>(src) + ((size_t)ch * Ptot0 + row0) * 16,
+                             (uint32_t)LC_ROWS * 16u, full);
+            };
+            for (int k = 0; k < n_my; ++k) {
+                const int it = (int)blockIdx.x + k * (int)gridDim.x;
+                if (MODE == 1) { mbar_wait(bar(LCB_X_FREE), (k & 1) ^ 1); load_act(it, p.x_hi, 0, bar(LCB_X_FULL)); }
+                if (MODE == 0) {       // 29 image rows of the 1-channel input: rows 0..28 (top item) or 19..47 (bottom item)
+                    mbar_wait(bar(LCB_TWIN_EMPTY), (k & 1) ^ 1);
+                    mbar_expect_tx(bar(LCB_TWIN_FULL), (uint32_t)LC_TWIN_BYTES);
+                    bulk_g2s(smem_u32(twin), p.t + (size_t)(it >> 1) * NPIX + (size_t)((it & 1) ? (LC_BOT_Y0 - 1) * STAMP : 0), (uint32_t)LC_TWIN_BYTES,
+                             bar(LCB_TWIN_FULL));
+                }
+                load_w(k, 0);
+                if (MODE == 1) { mbar_wait(bar(LCB_T_FREE), (k & 1) ^ 1); load_act(it, p.x_lo, 4, bar(LCB_T_FULL)); }
+                load_w(k, 1); load_w(k, 2); load_w(k, 3);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = instr_desc_f16(MTILE, LC_C);
+        const uint64_t a_desc0 = smem_desc(smem_u32(smem), LC_PSTRIDE * 16, 128);
+        const uint64_t w_desc0 = smem_desc(smem_u32(w_smem), LC_C * 16, 128);
+        constexpr uint32_t A_KK = 2 * LC_PSTRIDE, W_KK = 2 * LC_C, W_TAP = 4 * LC_C;   // in 16-byte units
+        uint32_t g = 0;                                   // running tile counter of this CTA (accumulator stage = g & 1)
+        for (int k = 0; k < n_my; ++k) {
+            const int it = (int)blockIdx.x + k * (int)gridDim.x, h = it & 1;
+            const uint32_t kp = (uint32_t)(k & 1);
+            for (int L = 0; L < 4; ++L) {
+                const int Lc = 4 * k + L, slot = Lc & 1;
+                mbar_wait(bar(LCB_W_FULL + slot), (Lc >> 1) & 1);
+                const int n = lc_ntiles(L), nprev = L == 0 ? LC_HEAD_TILES : lc_ntiles(L - 1);
+                const int src_pl = (L & 1) ? 4 : 0;       // conv 1 of a block reads X, conv 2 reads T
+                int pw = 0;
+                if (MODE == 1 && L == 0) mbar_wait(bar(LCB_X_FULL), kp);
+                for (int u0 = 0; u0 < n; u0 += LC_J) {
+                    const int nj = n - u0 < LC_J ? n - u0 : LC_J;
+                    int rj[LC_J];
+#pragma unroll
+                    for (int j = 0; j < LC_J; ++j) rj[j] = lc_tile_start(L, h, u0 + (j < nj ? j : nj - 1));
+                    // rows [r - 50, r + 178) of the input of every tile of the unit must be complete
+                    if (!(MODE == 1 && L == 0)) {
+                        while (pw < nprev && (L == 0 ? lc_head_start(h, pw) : lc_tile_start(L - 1, h, pw)) < rj[nj - 1] + MTILE + LC_WP + 1) {
+                            mbar_wait(bar(L == 0 ? LCB_X_READY + pw : LCB_TILE_DONE + (L - 1) * 11 + pw), kp);
+                            ++pw;
+                        }
+                    }
+                    const uint32_t b = g & 1;
+                    mbar_wait(bar(LCB_ACC_EMPTY + b), ((g >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d0 = tmem + (uint32_t)(LC_ACC_COL + b * (LC_J * LC_C));
+                    const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(src_pl * LC_PSTRIDE + LC_GAP);
+                    const uint64_t wd = w_desc0 + (uint64_t)((uint32_t)slot * (LC_W_BYTES >> 4));
+                    if (elect_one()) {
+                        // tap-major over the tiles of the unit: consecutive MMAs go to different accumulators, so the tensor pipe
+                        // overlaps them (measured: 18 back-to-back MMAs into ONE accumulator run at ~70 instead of ~41 cycles each, and so does the
+                        // second K16 step of a tap when it directly follows the first)
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                            for (int kk = 0; kk < 2; ++kk) {             // K = 32 channels = two K16 steps (chunk planes 2 kk, 2 kk + 1)
+                                const uint64_t bt = wd + (uint64_t)(tap * W_TAP + kk * W_KK);
+#pragma unroll
+                                for (int j = 0; j < LC_J; ++j) {         // innermost: back-to-back MMAs never share an accumulator
+                                    if (j < nj) {
+                                        const uint32_t d = d0 + (uint32_t)(j * LC_C);
+                                        const uint64_t at = ad + (uint64_t)(int64_t)(rj[j] + (tap / 3 - 1) * LC_WP + (tap % 3 - 1) + kk * (int)A_KK);
+                                        if (tap == 0 && kk == 0) tc_mma_f16(d, at, bt, idesc, 0u); else tc_mma_f16_acc(d, at, bt, idesc);
+                                    }
+                                }
+                            }
+                        }
+                        tc_commit(bar(LCB_ACC_FULL + b));
+                    }
+                    __syncwarp();
+                    ++g;
+                }
+                if (elect_one()) {
+                    tc_commit(bar(LCB_W_EMPTY + slot));
+                    if (L == 2) tc_commit(bar(LCB_X_FREE));
+                    if (L == 3) tc_commit(bar(LCB_T_FREE));
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 6) {
+        // ===== helpers =====
+        // DOWN, phase A (as soon as the previous item's last reads of X are done, i.e. during its 4th conv): x1 = m_head(t) -> X (fp16);
+        //       phase B (once the previous item's stream has been consumed): the same fp32 values -> stream (TMEM).  Recomputing the
+        //       288 FMAs per row is cheaper than holding them, and neither phase is on the MMA warp's critical path.
+        // UP:   stream = hi (X) + lo (T), which also releases T for the first conv's output.
+        const int q = warp & 3;
+        for (int k = 0; k < n_my; ++k) {
+            const int it = (int)blockIdx.x + k * (int)gridDim.x, h = it & 1;
+            const uint32_t kp = (uint32_t)(k & 1);
+            if (MODE == 0) {
+                const int ylo = h ? LC_BOT_Y0 - 1 : 0;                   // first image row held by the t window
+                // x1 of local row s (zeros outside the window / on pad pixels)
+                auto head_row = [&](int s, float* acc) -> bool {
+                    const int yq = s >= 0 ? (s * 1338) >> 16 : 0, x = s - yq * LC_WP;
+                    const bool inimg = s >= 0 && s < LC_ROWS && x < STAMP;
+                    const int y = h * LC_BOT_Y0 + yq;
+                    float in[9];
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int yy = y + dy, xx = x + dx;
+                            in[(dy + 1) * 3 + dx + 1] = (inimg && yy >= 0 && yy < STAMP && xx >= 0 && xx < STAMP) ? twin[(yy - ylo) * STAMP + xx] : 0.f;
+                        }
+#pragma unroll
+                    for (int c = 0; c < LC_C; ++c) acc[c] = 0.f;
+#pragma unroll
+                    for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+                        for (int c = 0; c < LC_C; ++c) acc[c] = fmaf(in[tp], htw.head[tp * LC_C + c], acc[c]);
+                    return inimg;
+                };
+                mbar_wait(bar(LCB_X_FREE), kp ^ 1);                      // the previous item's last reads of X have completed
+                mbar_wait(bar(LCB_TWIN_FULL), kp);
+                for (int j = 0; j < LC_HEAD_TILES; ++j) {
+                    const int s = lc_head_start(h, j) + q * 32 + lane;
+                    float acc[LC_C];
+                    if (head_row(s, acc)) {
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(smem + row_off(ch, s)) = pack8_half(acc + 8 * ch);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(LCB_X_READY + j));
+                }
+                mbar_wait(bar(LCB_ITEM_DONE), kp ^ 1);                   // the previous item's stream has been consumed
+                tc_fence_after();
+                for (int i = 0; i < LC_STREAM_TILES; ++i) {
+                    const int s = lc_stream_start(h, i) + q * 32 + lane;
+                    float acc[LC_C];
+                    head_row(s, acc);
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * LC_C);
+                    uint32_t u[LC_C];
+#pragma unroll
+                    for (int c = 0; c < LC_C; ++c) u[c] = __float_as_uint(acc[c]);
+                    tc_st16(taddr, u); tc_st16(taddr + 16, u + 16);
+                    tc_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(LCB_S_READY + i));
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(LCB_TWIN_EMPTY));
+            } else {
+                mbar_wait(bar(LCB_ITEM_DONE), kp ^ 1);
+                mbar_wait(bar(LCB_X_FULL), kp);
+                mbar_wait(bar(LCB_T_FULL), kp);
+                tc_fence_after();
+                for (int i = 0; i < LC_STREAM_TILES; ++i) {
+                    const int s = lc_stream_start(h, i) + q * 32 + lane;
+                    uint32_t u[LC_C];
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const uint4 hi = *reinterpret_cast<const uint4*>(smem + row_off(ch, s));
+                        const uint4 lo = *reinterpret_cast<const uint4*>(smem + row_off(4 + ch, s));
+                        const float2 f0 = hilo_pair(hi.x, lo.x), f1 = hilo_pair(hi.y, lo.y), f2 = hilo_pair(hi.z, lo.z), f3 = hilo_pair(hi.w, lo.w);
+                        u[8 * ch] = __float_as_uint(f0.x); u[8 * ch + 1] = __float_as_uint(f0.y); u[8 * ch + 2] = __float_as_uint(f1.x); u[8 * ch + 3] = __float_as_uint(f1.y);
+                        u[8 * ch + 4] = __float_as_uint(f2.x); u[8 * ch + 5] = __float_as_uint(f2.y); u[8 * ch + 6] = __float_as_uint(f3.x); u[8 * ch + 7] = __float_as_uint(f3.y);
+                    }
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * LC_C);
+                    tc_st16(taddr, u); tc_st16(taddr + 16, u + 16);
+                    tc_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(bar(LCB_X_READY + i)); mbar_arrive(bar(LCB_S_READY + i)); }   // the lo rows of stream tile i may be overwritten (T)
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: group (warps 6-9 / 10-13) takes every second UNIT of the CTA-wide sequence; a warp walks the unit's tiles =====
+        const int q = warp & 3, grp = (warp - 6) >> 2;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        uint32_t g = 0;
+        for (int k = 0; k < n_my; ++k) {
+            const int it = (int)blockIdx.x + k * (int)gridDim.x, bst = it >> 1, h = it & 1;
+            const uint32_t kp = (uint32_t)(k & 1);
+            for (int L = 0; L < 4; ++L) {
+                const int n = lc_ntiles(L);
+                for (int u0 = 0; u0 < n; u0 += LC_J, ++g) {
+                    if ((int)(g & 1) != grp) continue;
+                    const int nj = n - u0 < LC_J ? n - u0 : LC_J;
+                    const uint32_t b = g & 1;
+                    mbar_wait(bar(LCB_ACC_FULL + b), (g >> 1) & 1);
+                    tc_fence_after();
+                    for (int j = 0; j < nj; ++j) {
+                        const int i = u0 + j;
+                        int r, wlo, whi;
+                        lc_tile(L, h, i, r, wlo, whi);
+                        const uint32_t acc_addr = tmem + lane_base + (uint32_t)(LC_ACC_COL + b * (LC_J * LC_C) + j * LC_C);
+                        const uint32_t st_addr = tmem + lane_base + (uint32_t)(i * LC_C);     // layers 1, 3 run on the stream grid
+                        uint32_t r0[16], r1[16], s0[16], s1[16];
+                        tc_ld16_nowait(acc_addr, r0);
+                        tc_ld16_nowait(acc_addr + 16, r1);
+                        if (L == 1) { mbar_wait(bar(LCB_S_READY + i), kp); tc_fence_after(); }   // the helpers have filled this stream tile
+                        if (L & 1) { tc_ld16_nowait(st_addr, s0); tc_ld16_nowait(st_addr + 16, s1); }
+                        const int s = r + q * 32 + lane;
+                        const int yq = (s * 1338) >> 16, x = s - yq * LC_WP;       // s / 49 exactly for 0 <= s < 2400
+                        const bool inimg = s < LC_ROWS && x < STAMP;
+                        const bool wr = inimg && s >= wlo && s < whi;
+                        tc_ld_wait16(r0);
+                        tc_ld_wait16(r1);
+                        if (L & 1) { tc_ld_wait16(s0); tc_ld_wait16(s1); }
+                        if (j == nj - 1) {               // every accumulator of the unit has been read: the MMA warp may reuse the stage
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar(LCB_ACC_EMPTY + b));
+                        }
+                        float v[LC_C];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) { v[c] = __uint_as_float(r0[c]); v[16 + c] = __uint_as_float(r1[c]); }
+                        if (!(L & 1)) {
+                            // first conv of a block: ReLU -> fp16 -> T
+                            if (MODE == 1 && L == 0) {       // T still holds the lo halves until the helpers have moved them into the stream
+                                for (int si = 0; si < LC_STREAM_TILES; ++si) {
+                                    const int ss = lc_stream_start(h, si);
+                                    if (ss < r + MTILE && ss + MTILE > r) mbar_wait(bar(LCB_X_READY + si), kp);
+                                }
+                            }
+                            if (wr) {
+#pragma unroll
+                                for (int c = 0; c < LC_C; ++c) v[c] = fmaxf(v[c], 0.f);
+#pragma unroll
+                                for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(smem + row_off(4 + ch, s)) = pack8_half(v + 8 * ch);
+                            }
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar(LCB_TILE_DONE + L * 11 + i));
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) { v[c] += __uint_as_float(s0[c]); v[16 + c] += __uint_as_float(s1[c]); }
+                            if (L == 1) {
+                                // second conv of block 1: stream += acc (TMEM), fp16 copy -> X
+                                uint32_t u[LC_C];
+#pragma unroll
+                                for (int c = 0; c < LC_C; ++c) u[c] = __float_as_uint(v[c]);
+                                tc_st16(st_addr, u); tc_st16(st_addr + 16, u + 16);
+                                if (wr) {
+#pragma unroll
+                                    for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(smem + row_off(ch, s)) = pack8_half(v + 8 * ch);
+                                }
+                                tc_st_wait();
+                                tc_fence_before();
+                                fence_proxy_async_smem();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(bar(LCB_TILE_DONE + L * 11 + i));
+                            } else {
+                                // second conv of block 2: the item's own 24 rows leave the SM
+                                const bool own = wr && (h ? s >= LC_ROWS - LC_OWN : s < LC_OWN);
+                                if (own) {
+                                    const int y = h * LC_BOT_Y0 + yq;
+                                    if (MODE == 0) {
+                                        const Geom& g1 = p.g1;
+                                        const int crow = g1.base0 + bst * g1.S + (y >> 1) * g1.Wp + (x >> 1), ctap = ((y & 1) << 1) | (x & 1);
+                                        uint4* dst = reinterpret_cast<uint4*>(p.s2d) + (size_t)(ctap * 4) * g1.Ptot + crow;
+#pragma unroll
+                                        for (int ch = 0; ch < 4; ++ch) dst[(size_t)ch * g1.Ptot] = pack8_half(v + 8 * ch);
+                                    } else {
+                                        float* dst = p.tail_part + ((size_t)p.g0.base0 + (size_t)bst * p.g0.S + (size_t)(y * LC_WP + x));
+                                        lc_tail(htw.tail, v, dst, Ptot0);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(LCB_ITEM_DONE));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+static int g_lc_sms = 0;
+
+int conv_l1chain_init() {
+    int dev;
+    GD_CUDA_CHECK(cudaGetDevice(&dev));
+    GD_CUDA_CHECK(cudaDeviceGetAttribute(&g_lc_sms, cudaDevAttrMultiProcessorCount, dev));
+    GD_CUDA_CHECK(cudaFuncSetAttribute(k_l1_chain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM));
+    GD_CUDA_CHECK(cudaFuncSetAttribute(k_l1_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM));
+    return GD_OK;
+}
+
+static int l1chain_launch(int mode, const L1ChainParams& p, const float* head_w, const float* tail_w, cudaStream_t st) {
+    if (p.nb <= 0) return GD_OK;
+    if (!g_lc_sms) { set_error("conv_l1chain: library not initialised"); return GD_ECUDA; }
+    if (p.g0.Wp != LC_WP || p.g0.base0 < LC_WP + 1 || p.g1.Wp != 25) { set_error("conv_l1chain: needs the 48x48 / 24x24 geometries"); return GD_EUNSUPPORTED; }
+    L1ChainHT hw;
+    memset(&hw, 0, sizeof(hw));
+    if (head_w) memcpy(hw.head, head_w, sizeof(hw.head));
+    if (tail_w) memcpy(hw.tail, tail_w, sizeof(hw.tail));
+    const int items = 2 * p.nb, grid = items < g_lc_sms ? items : g_lc_sms;
+    cudaEvent_t e1 = nullptr;
+    const double flops = 4.0 * 2.0 * (double)p.nb * NPIX * (double)LC_C * LC_C * 9;      // four 3x3 convs, valid pixels
+    { int rc = conv_profile_mark(flops, st, &e1); if (rc != GD_OK) return rc; }
+    if (mode == 0) k_l1_chain<0><<<grid, LC_THREADS, LC_SMEM, st>>>(p, hw);
+    else k_l1_chain<1><<<grid, LC_THREADS, LC_SMEM, st>>>(p, hw);
+    GD_LAUNCHED();
+    if (e1) GD_CUDA_CHECK(cudaEventRecord(e1, st));
+    return GD_OK;
+}
+
+int launch_l1chain_down(const Geom& g0, const Geom& g1, int nb, const float* t, const float* head_w_host, const void* const* w4, void* s2d,
+                        cudaStream_t st) {
+    L1ChainParams p;
+    memset(&p, 0, sizeof(p));
+    p.nb = nb; p.g0 = g0; p.g1 = g1; p.t = t; p.s2d = s2d;
+    for (int i = 0; i < 4; ++i) p.w[i] = w4[i];
+    if (!t || !head_w_host || !s2d) { set_error("conv_l1chain: down needs t, the head weights and the s2d target"); return GD_EBADSHAPE; }
+    return l1chain_launch(0, p, head_w_host, nullptr, st);
+}
+
+int launch_l1chain_up(const Geom& g0, const Geom& g1, int nb, const void* x_hi, const void* x_lo, const float* tail_w_host, const void* const* w4,
+                      float* tail_part, cudaStream_t st) {
+    L1ChainParams p;
+    memset(&p, 0, sizeof(p));
+    p.nb = nb; p.g0 = g0; p.g1 = g1; p.x_hi = x_hi; p.x_lo = x_lo; p.tail_part = tail_part;
+    for (int i = 0; i < 4; ++i) p.w[i] = w4[i];
+    if (!x_hi || !x_lo || !tail_w_host || !tail_part) { set_error("conv_l1chain: up needs the hi/lo stream, the tail weights and tail_part"); return GD_EBADSHAPE; }
+    return l1chain_launch(1, p, nullptr, tail_w_host, st);
+}
+
+}  // namespace gd

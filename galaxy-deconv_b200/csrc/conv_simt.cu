@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(TAIL_ROWS) k_tail(const float* __restrict__ x3
 struct TailG { float g[81]; };
 __global__ void __launch_bounds__(256) k_tail_gather(const float* __restrict__ P, int units, Geom g, const float* __restrict__ tscale,
                                                      float* __restrict__ z, int batch, const float* __restrict__ tpad, int has_g,
-                                                     const __grid_constant__ TailG G) {
+                                                     const __grid_constant__ TailG G, int t_plain) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= batch * NPIX) return;
     const int b = idx / NPIX, r = idx - b * NPIX, y = r / STAMP, x = r - y * STAMP;
@@ -206,7 +206,9 @@ __global__ void __launch_bounds__(256) k_tail_gather(const float* __restrict__ P
 #pragma unroll
             for (int dx = -2; dx <= 2; ++dx) {
                 const int yy = y + dy, xx = x + dx;
-                tt[(dy + 2) * 5 + dx + 2] = (yy >= 0 && yy < STAMP && xx >= 0 && xx < STAMP) ? __ldg(tpad + row + dy * g.Wp + dx) : 0.f;
+                // t_plain: `tpad` is the dense [B][48*48] denoiser input itself (conv_l1chain.cu path: no padded-linear copy exists)
+                tt[(dy + 2) * 5 + dx + 2] = (yy >= 0 && yy < STAMP && xx >= 0 && xx < STAMP)
+                                                ? (t_plain ? __ldg(tpad + (size_t)b * NPIX + yy * STAMP + xx) : __ldg(tpad + row + dy * g.Wp + dx)) : 0.f;
             }
 #pragma unroll
         for (int t2 = 0; t2 < 9; ++t2) {
@@ -248,12 +250,12 @@ int launch_head(const float* t, const float* w, const float* w_host, int C0, con
 }
 
 int launch_tail_gather(const float* P, int units, const Geom& g, const float* tscale, float* z, int batch, const float* tpad,
-                       const float* G81_host, cudaStream_t st) {
+                       const float* G81_host, cudaStream_t st, int t_plain) {
     if (batch <= 0) return GD_OK;
     TailG G;
     memset(&G, 0, sizeof(G));
     if (G81_host) memcpy(G.g, G81_host, sizeof(G.g));
-    k_tail_gather<<<(batch * NPIX + 255) / 256, 256, 0, st>>>(P, units, g, tscale, z, batch, tpad, G81_host != nullptr, G);
+    k_tail_gather<<<(batch * NPIX + 255) / 256, 256, 0, st>>>(P, units, g, tscale, z, batch, tpad, G81_host != nullptr, G, t_plain);
     GD_LAUNCHED();
     return GD_OK;
 }

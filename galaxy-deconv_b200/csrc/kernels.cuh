@@ -16,6 +16,11 @@ void conv_profile_begin();
 int conv_profile_end(double* ms_total, double* flops_total, unsigned long long* launches);
 int conv_profile_mark(double flops, cudaStream_t st, cudaEvent_t* stop);
 int conv_rb_init();
+int conv_l1chain_init();
+int launch_l1chain_down(const Geom& g0, const Geom& g1, int nb, const float* t, const float* head_w_host, const void* const* w4, void* s2d,
+                        cudaStream_t st);
+int launch_l1chain_up(const Geom& g0, const Geom& g1, int nb, const void* x_hi, const void* x_lo, const float* tail_w_host, const void* const* w4,
+                      float* tail_part, cudaStream_t st);
 bool conv_rb_supported(const ConvParams& p1, const ConvParams& p2);
 int launch_conv_rb(const ConvParams& p1, const ConvParams& p2, cudaStream_t st);
 
@@ -46,7 +51,7 @@ int launch_conv_simt(const ConvParams& p, int prec, cudaStream_t st);
 int launch_conv_umma(const ConvParams& p, cudaStream_t st);
 int launch_head(const float* t, const float* w, const float* w_host, int C0, const ConvParams& p, int batch, int prec, float* tpad, cudaStream_t st);
 int launch_tail_gather(const float* P, int units, const Geom& g, const float* tscale, float* z, int batch, const float* tpad,
-                       const float* G81_host, cudaStream_t st);
+                       const float* G81_host, cudaStream_t st, int t_plain = 0);
 int launch_tail(const float* x32, const float* w, int C0, const Geom& g, const float* tscale, float* z, int batch,
                 cudaStream_t st);
 

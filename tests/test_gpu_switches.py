@@ -44,6 +44,7 @@ print(json.dumps({'golden': err_golden, 'big': err_big, 'finite': bool(torch.isf
 
 VARIANTS = [
     {},
+    {'GDECONV_L1CHAIN': '0'},
     {'GDECONV_FUSE_RB': '0'},
     {'GDECONV_FUSE_RB': '2'},
     {'GDECONV_HILO': '0'},
@@ -56,6 +57,7 @@ VARIANTS = [
     {'GDECONV_RESMMA': '1'},
     {'GDECONV_LATEPF': '1'},
     {'GDECONV_FUSE_RB': '0', 'GDECONV_HILO': '0', 'GDECONV_FUSE_HT': '0', 'GDECONV_CLUSTER': '1'},
+    {'GDECONV_L1CHAIN': '0', 'GDECONV_FUSE_RB': '0'},
 ]
 
 
