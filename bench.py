@@ -11,12 +11,19 @@ their NCCL all-gather.  Weak scaling: every rank processes its own `stamps` gala
 
 Printed JSON (rank 0, one line): `value` = whole-job galaxies/s with inputs resident in HBM; `e2e` = the same call with
 pinned HOST inputs (H2D of obs/psf/alpha and D2H of the deconvolved stamps + ellipticities inside the timed region);
-`roofline` = the dominant kernel (k_conv_umma and its fused-ResBlock sibling k_rb_umma, tcgen05 tap-GEMM) timed live per launch with CUDA events, algorithmic
+`roofline` = the dominant kernel family (k_conv_umma and the level-0 chain kernel k_l1_chain, tcgen05 tap-GEMM) timed live per launch with CUDA events, algorithmic
 FLOPs / time against the measured bf16 peak of MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle (bit-exact port of
 the reference's torch code) timed on this box's host cores on a bounded sample.
 
 --impl reference: times the reference's own CPU implementation of the path (the oracle port; /root/reference does not
-exist on the GPU box) on the host cores with all threads; rank 0 only.
+exist on the GPU box) on the host cores with all threads; rank 0 only.  It imports only torch, the oracle and the
+torch-only generator module gdsynth: libgdeconv.so is never mapped in that process.
+
+--config 3|4|5 run the other BASELINE.json configs (one JSON line per measurement; the default line, config 2, is unchanged):
+  3  Unrolled-ADMM(8) on --total (1,000,000) stamps, STRONG scaling: the total is sharded by galaxy over the ranks, every shard
+     is generated on its own GPU, and one step = forward over the whole shard + moment ellipticities + NCCL all-gather;
+  4  Richardson-Lucy(10/50/100), Wiener, Tikhonov-Laplacian and Tikhonet_Laplacian on --total stamps, sharded the same way;
+  5  PSF-mismatch sweep (test_psf.py:237-242 shape): 10 shear + 10 seeing errors x --sweep-stamps (100,000) stamps, sharded.
 """
 from __future__ import annotations
 
@@ -30,7 +37,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path[:0] = [os.path.join(ROOT, 'galaxy-deconv_b200'), ROOT]
+sys.path[:0] = [os.path.join(ROOT, 'galaxy-deconv_b200'), ROOT, os.path.join(ROOT, 'tools')]
 
 import torch  # noqa: E402
 
@@ -97,7 +104,7 @@ class ClockSampler:
 def cpu_reference(n_iters, sample, batch, steps, warmup):
     """The reference's CPU implementation of the path (oracle port, bit-exact vs the reference) on the host cores."""
     import oracle.ref_models as O
-    from gdeconv.synth import make_batch
+    from gdsynth import make_batch            # torch-only module: the reference arm never loads libgdeconv.so
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     m = O.UnrolledADMMGaussian(n_iters).eval()
@@ -126,7 +133,10 @@ def main():
     ap.add_argument('--stamps', type=int, default=10000, help='stamps per GPU per step')
     ap.add_argument('--n-iters', type=int, default=8)
     ap.add_argument('--precision', default=None)
-    ap.add_argument('--cpu-sample', type=int, default=128)
+    ap.add_argument('--cpu-sample', type=int, default=512, help='stamps per pass of the cpu_baseline leg (BASELINE.md section 3: N = 512)')
+    ap.add_argument('--config', type=int, default=2, choices=[2, 3, 4, 5], help='BASELINE.json configs index (2 = headline)')
+    ap.add_argument('--total', type=int, default=1000000, help='configs 3/4: total stamps over all ranks')
+    ap.add_argument('--sweep-stamps', type=int, default=100000, help='config 5: stamps per sweep point over all ranks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
@@ -141,7 +151,9 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        r = cpu_reference(args.n_iters, 64, 64, max(1, args.steps), min(1, args.warmup))
+        # a step = one pass over a bounded sample of the workload, sized so that steps + warm-up stay within ~2 minutes
+        per_step = max(64, min(512, int(15000 / max(1, args.steps + args.warmup)) // 64 * 64))
+        r = cpu_reference(args.n_iters, per_step, 64, max(1, args.steps), max(0, args.warmup))
         print(json.dumps(dict(metric=metric, value=r['value'], unit='galaxies/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                               ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
                               data='synthetic', impl='reference', config=cfg,
@@ -153,7 +165,7 @@ def main():
     from gdeconv import engine, moments_e
     from gdeconv._lib import lib
     from gdeconv.shard import gather_ellipticities, shard_range
-    from gdeconv.synth import make_batch
+    from gdsynth import make_batch
     from models.unrolled_admm_gaussian import UnrolledADMMGaussian
     import oracle.ref_models as O          # only for the seeded weights and the cpu_baseline leg
 
@@ -169,6 +181,12 @@ def main():
     model = UnrolledADMMGaussian(args.n_iters).eval()
     model.load_state_dict(O.seeded_state_dict(lambda: O.UnrolledADMMGaussian(args.n_iters), 12))
     model = model.to(dev)
+    if args.config != 2:
+        from bench_configs import run_config
+        run_config(args, model, dev, rank, world, peaks())
+        if world > 1:
+            dist.destroy_process_group()
+        return
     n_total = args.stamps * world
     lo, hi = shard_range(n_total, rank, world)
     data = make_batch(lo, hi - lo, 100.0, device=dev)
@@ -182,12 +200,10 @@ def main():
         return gather_ellipticities(moments_e(out), n_total)
 
     def step_e2e():
-        o = host['obs'].to(dev, non_blocking=True)
-        p = host['psf'].to(dev, non_blocking=True)
-        a = host['alpha'].to(dev, non_blocking=True)
-        out = model(o, p, a)
-        e = gather_ellipticities(moments_e(out), n_total)
-        out_host.copy_(out, non_blocking=True)
+        # the public host-batch call: chunk-pipelined H2D / compute / D2H inside the engine (one cudaMemcpyAsync per tensor and
+        # chunk on two copy streams), then the ellipticity gather and its D2H
+        _, e_loc = model.deconvolve_host(host['obs'], host['psf'], host['alpha'], out=out_host, want_e=True, device=dev)
+        e = gather_ellipticities(e_loc, n_total)
         e_host.copy_(e, non_blocking=True)
 
     def timed(fn, steps, warmup):
@@ -215,7 +231,7 @@ def main():
     with ClockSampler(local) as clk:
         ms_step, launches = timed(step_device, args.steps, max(3, args.warmup))
     clocks = clk.summary()
-    ms_e2e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
+    ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup))
 
     # dominant kernel, live: every k_conv_umma / k_rb_umma launch of one more step bracketed by CUDA events on its stream
     roof = None
@@ -250,7 +266,7 @@ def main():
                 pass
             roof = dict(bound='tensor', achieved=ach, peak=P['tensor_sustained'], unit='TFLOP/s', frac=ach / P['tensor_sustained'], traffic=traffic,
                         traffic_note=traffic_note,
-                        kernel='k_conv_umma + k_rb_umma (tcgen05 tap-GEMM convolutions)', launches_per_step=int(n_k.value), avg_launch_us=ms_k.value * 1e3 / max(1, n_k.value),
+                        kernel='k_conv_umma + k_l1_chain (tcgen05 tap-GEMM convolutions; k_l1_chain = 4 convs per launch)', launches_per_step=int(n_k.value), avg_launch_us=ms_k.value * 1e3 / max(1, n_k.value),
                         kernel_share_of_step=ms_k.value / ms_profile_step, profiled_step_ms=ms_profile_step, flops_per_launch_avg=fl_k.value / max(1, n_k.value),
                         peak_source=P['source'] + ', sustained bf16 (kernel timed inside a long step); burst = %.1f' % P['tensor_burst'])
 
@@ -271,7 +287,7 @@ def main():
     if roof:
         line['roofline'] = roof
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(args.n_iters, args.cpu_sample, 64, 1, 1)
+        r = cpu_reference(args.n_iters, args.cpu_sample, 64, 3, 1)
         line['cpu_baseline'] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     print(json.dumps(line))
     if world > 1:

@@ -180,7 +180,6 @@ static int init_once(int device) {
     GD_TRY(fft_kernels_init());
     GD_TRY(subnet_init());
     GD_TRY(conv_umma_init());
-    GD_TRY(conv_chain_init());
     GD_TRY(conv_rb_init());
     GD_TRY(conv_l1chain_init());
     done.fetch_or(1u << device);
@@ -353,7 +352,6 @@ struct Ws {
     // ResUNet activations
     float *skip32[4], *p32a[4], *p32b[4];
     void *a16[4], *t16[4], *d16[4], *lo16[4];   // lo16: fp16 correction planes of the hi/lo residual stream (hi = a16 / t16)
-    unsigned int* chain_flags;                 // per-(layer, item) completion counters of the layer-chained kernel
     float *tpad, *tail_part;                   // head/tail fusion (conv_umma.cu EPI_HT): padded-linear input, per-tap tail sums
 };
 
@@ -388,7 +386,6 @@ static Ws ws_layout(unsigned char* base, int arch, int prec, int chunk) {
         w.lo16[L] = take(n * es);
         if (L > 0) w.d16[L] = take((size_t)2 * n * es);        // 4*C_{L-1} = 2*C_L channels
     }
-    w.chain_flags = (unsigned int*)take(chain_flag_words(w.g[0].Ptot) * sizeof(unsigned int));
     w.tpad = (float*)take((size_t)w.g[0].Ptot * 4);
     w.tail_part = (float*)take((size_t)(C0 / 16) * 9 * w.g[0].Ptot * 4);   // 32-channel units (conv_umma.cu) or 16-channel halves (conv_rb.cu)
     w.total = off;
@@ -440,18 +437,6 @@ static int run_conv(const ConvParams& p, int prec, cudaStream_t st) {
     return prec == PREC_FP16_UMMA ? launch_conv_umma(p, st) : launch_conv_simt(p, prec, st);
 }
 
-// Sub-chunking: the wide, shallow levels 0-1 (48x48 and 24x24, ~1.2 MB of activations per stamp) are walked
-// sub-chunk by sub-chunk so that a sub-chunk's working set stays in the 126 MB L2 across consecutive layers, while
-// the narrow, deep levels 2-3 run over the whole chunk at once (enough 128-row tiles to fill 148 SMs).
-static int g_chain = -1;
-static int chain_mode() {
-    if (g_chain < 0) {
-        const char* e = getenv("GDECONV_CHAIN");
-        g_chain = e ? atoi(e) : 0;               // 1: layer-chained launches at the 32- and 64-channel levels (conv_chain.cu);
-                                                 // off by default: measured 7 % slower than one launch per layer (profiles/)
-    }
-    return g_chain;
-}
 // Head/tail fusion of the tcgen05 path (GDECONV_FUSE_HT=0 restores the stored fp32 head output and the k_tail kernel).
 static int g_fuse_ht = -1;
 static int fuse_ht_mode() {
@@ -488,15 +473,6 @@ static int tail_g_mode() {
     }
     return g_tailg;
 }
-static int g_subchunk = 0;
-static int subchunk_size() {
-    if (!g_subchunk) {
-        const char* e = getenv("GDECONV_SUBCHUNK");
-        g_subchunk = e && atoi(e) > 0 ? atoi(e) : (1 << 30);     // default: no sub-chunking (measured slower, profiles/)
-    }
-    return g_subchunk;
-}
-
 // m_head fused into k_g_xupdate (path G, tcgen05, C0 = 32, head/tail fusion); GDECONV_XHEAD=0: separate k_head32 launch
 static int g_xhead = -1;
 static int xhead_mode() {
@@ -518,8 +494,7 @@ static int l1chain_mode() {
 }
 static int g_fuse_ht_fwd();
 static bool l1chain_applies(const GdWeights* W) {
-    return l1chain_mode() && W->precision == PREC_FP16_UMMA && W->nc[0] == 32 && g_fuse_ht_fwd() && hilo_mode() && tail_g_mode() &&
-           subchunk_size() >= (1 << 30);
+    return l1chain_mode() && W->precision == PREC_FP16_UMMA && W->nc[0] == 32 && g_fuse_ht_fwd() && hilo_mode() && tail_g_mode();
 }
 static bool xhead_applies(const GdWeights* W) {
     return xhead_mode() && W->precision == PREC_FP16_UMMA && W->nc[0] == 32 && g_fuse_ht_fwd() && !l1chain_applies(W);
@@ -535,8 +510,8 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         return base ? (unsigned char*)base + (size_t)s0 * g[L].S * 16 : nullptr;
     };
     // tcgen05 path: x1 is never stored in fp32; its consumers recompute it from tpad (ConvParams::head_t)
-    const bool fuse = prec == PREC_FP16_UMMA && !chain_mode() && fuse_ht_mode() && C[0] <= 64;
-    const bool hilo = prec == PREC_FP16_UMMA && !chain_mode() && hilo_mode();
+    const bool fuse = prec == PREC_FP16_UMMA && fuse_ht_mode() && C[0] <= 64;
+    const bool hilo = prec == PREC_FP16_UMMA && hilo_mode();
     const bool l1chain = l1chain_applies(W);      // level 0 runs in the two chain kernels: no separate head launch, no level-0 fp32 buffers
     if (!l1chain) {   // head (ResUNet.py:31): x1 = conv(t)  -> skip32[0] (fp32) + a16[0]
         ConvParams p = conv_base(g[0], nb);
@@ -581,11 +556,10 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
             if (is_stream(p[1].res32)) { p[1].res_hi = p[0].a; p[1].res_lo = at(ws.lo16[L], L, s0); p[1].res32 = nullptr; }
             if (is_stream(p[1].out32) && p[1].out16) { p[1].out_lo = at(ws.lo16[L], L, s0); p[1].out32 = nullptr; }
         }
-        if (prec == PREC_FP16_UMMA && chain_mode() && C[L] == 64) return launch_conv_chain(p, 2, ws.chain_flags, st);
         // fused kernel, except (mode 1) for the two ResBlocks whose epilogue recomputes m_head / reduces against m_tail: those
         // FMA-heavy epilogues are faster on the eight 32-channel epilogue warps of conv_umma.cu (profiles/README);
         // GDECONV_FUSE_RB=2 fuses them too
-        if (prec == PREC_FP16_UMMA && !chain_mode() && fuse_rb_mode() && conv_rb_supported(p[0], p[1]) &&
+        if (prec == PREC_FP16_UMMA && fuse_rb_mode() && conv_rb_supported(p[0], p[1]) &&
             (fuse_rb_mode() >= 2 || (!p[1].tail_part && !p[1].head_t)))
             return launch_conv_rb(p[0], p[1], st);
         if (p[0].a == p[0].out16 || p[1].a == p[1].out16) GD_FAIL(GD_EUNSUPPORTED, "resblock: in-place fp16 buffers need the fused kernel");
@@ -595,17 +569,11 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
     // two consecutive ResBlocks of one level: one chained launch when all four layers' weights fit in shared memory
     auto resblock_pair = [&](int L, int s0, int n, const void* const* wa, const void* const* wb, const float* res_a, float* out32_a,
                              void* out16_a, const float* res_b, const float* skip_b, float* out32_b, void* out16_b, void* s2d_b) -> int {
-        if (prec == PREC_FP16_UMMA && chain_mode() && C[L] == 32) {
-            ConvParams p[4];
-            rb_params(L, s0, n, wa, res_a, nullptr, out32_a, out16_a, nullptr, p);
-            rb_params(L, s0, n, wb, res_b, skip_b, out32_b, out16_b, s2d_b, p + 2);
-            return launch_conv_chain(p, 4, ws.chain_flags, st);
-        }
         const bool last_l0 = fuse && L == 0 && skip_b != nullptr;       // second ResBlock of m_up1: + x1, then m_tail
         const bool first_ht = fuse && L == 0 && res_a == ws.skip32[0];        // first ResBlock of m_down1: residual = x1
         if (first_ht) ht_res_is_head = true;
         // the first ResBlock writes its fp16 output to t16 when it runs in the fused kernel (no in-place halo race)
-        const bool pingpong = prec == PREC_FP16_UMMA && !chain_mode() && fuse_rb_mode() && C[L] == 32 && out16_a == ws.a16[L] &&
+        const bool pingpong = prec == PREC_FP16_UMMA && fuse_rb_mode() && C[L] == 32 && out16_a == ws.a16[L] &&
                               (fuse_rb_mode() >= 2 || !first_ht);
         GD_TRY(resblock(L, s0, n, wa, res_a, nullptr, out32_a, pingpong ? ws.t16[L] : out16_a, nullptr));
         if (last_l0) { ht_skip_is_head = !tail_g_mode(); ht_tail = true; ht_drop_skip = tail_g_mode() != 0; }
@@ -640,30 +608,23 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L], ws.skip32[L],
                              ws.p32a[L], nullptr, nullptr);
     };
-    const int sub = subchunk_size();
-    for (int s0 = 0; s0 < nb; s0 += sub) {
-        const int n = nb - s0 < sub ? nb - s0 : sub;
-        GD_TRY(down_stage(0, s0, n));
-        GD_TRY(down_stage(1, s0, n));
-    }
+    GD_TRY(down_stage(0, 0, nb));
+    GD_TRY(down_stage(1, 0, nb));
     GD_TRY(down_stage(2, 0, nb));
     // m_body (ResUNet.py:35) and the skip x + x4 (:36)
     GD_TRY(resblock(3, 0, nb, W->body_rb[0], ws.skip32[3], nullptr, ws.p32a[3], ws.a16[3], nullptr));
     GD_TRY(resblock(3, 0, nb, W->body_rb[1], ws.p32a[3], ws.skip32[3], nullptr, ws.a16[3], nullptr));
     GD_TRY(up_stage(2, 0, nb));
-    for (int s0 = 0; s0 < nb; s0 += sub) {
-        const int n = nb - s0 < sub ? nb - s0 : sub;
-        GD_TRY(up_stage(1, s0, n));
-        GD_TRY(up_stage(0, s0, n));
-    }
+    GD_TRY(up_stage(1, 0, nb));
+    GD_TRY(up_stage(0, 0, nb));
     // tail (ResUNet.py:39): conv(x + x1), times the per-stamp input scale
     if (l1chain) return launch_tail_gather(ws.tail_part, 1, g[0], tscale, zout, nb, t, W->tail_head_g, st, 1);
-    if (fuse) return launch_tail_gather(ws.tail_part, (!chain_mode() && fuse_rb_mode() >= 2 && C[0] == 32) ? 2 : C[0] / 32, g[0], tscale, zout, nb,
+    if (fuse) return launch_tail_gather(ws.tail_part, (fuse_rb_mode() >= 2 && C[0] == 32) ? 2 : C[0] / 32, g[0], tscale, zout, nb,
                                         ws.tpad, tail_g_mode() ? W->tail_head_g : nullptr, st);
     return launch_tail(ws.p32a[0], W->tail, C[0], g[0], tscale, zout, nb, st);
 }
 
-static int g_fuse_ht_fwd() { return !chain_mode() && fuse_ht_mode(); }
+static int g_fuse_ht_fwd() { return fuse_ht_mode(); }
 
 static int rho_chunk(const GdWeights* W, const Ws& ws, const float* psf, const float* alpha, int nb, cudaStream_t st) {
     if (W->has_subnet) return launch_subnet(W->sub, psf, alpha, ws.rho, nb, st);
@@ -678,15 +639,32 @@ static int copy_f32(float* dst, const float* src, size_t n, cudaStream_t st) {
 
 }  // namespace gd
 
+extern "C" int gd_max_chunk(void) {
+    // largest chunk whose level-0 GEMM rows (2401 per stamp + tile/halo slack) stay below the 2^26 limit of div_by_magic
+    int lo = 1, hi = 1 << 20;
+    while (lo < hi) { const int mid = lo + (hi - lo + 1) / 2; if (geom_rows_ok(STAMP, mid)) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+extern "C" long long gd_debug_divmagic(unsigned d, unsigned n_lo, unsigned n_hi) {
+    // host-side exhaustive check of the multiply-shift division the kernels decode rows with; -1 = exact on [n_lo, n_hi)
+    uint32_t magic, shift;
+    div_magic(d, &magic, &shift);
+    for (unsigned n = n_lo; n < n_hi; ++n)
+        if (div_by_magic(n, magic, shift) != n / d) return (long long)n;
+    return -1;
+}
+
 extern "C" size_t gd_workspace_bytes(int arch, int precision, int chunk) {
     if ((arch != GD_ARCH_G && arch != GD_ARCH_U) || precision < 0 || precision > 2 || chunk < 1) return 0;
+    if (!geom_rows_ok(STAMP, chunk)) return 0;            // row decode (div_by_magic) is only exact below 2^26 rows
     return ws_layout(nullptr, arch, precision, chunk).total;
 }
 
 extern "C" int gd_workspace_init(void* workspace, size_t bytes, int arch, int precision, int chunk, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     size_t need = gd_workspace_bytes(arch, precision, chunk);
-    if (!need) GD_FAIL(GD_EBADSHAPE, "bad workspace parameters (arch %d, precision %d, chunk %d)", arch, precision, chunk);
+    if (!need) GD_FAIL(GD_EBADSHAPE, "bad workspace parameters (arch %d, precision %d, chunk %d; the largest chunk is %d stamps)", arch, precision, chunk, gd_max_chunk());
     if (!workspace || bytes < need) GD_FAIL(GD_EWORKSPACE, "workspace of %zu bytes is smaller than the %zu needed for chunk %d", bytes, need, chunk);
     GD_CUDA_CHECK(cudaMemsetAsync(workspace, 0, need, st));
     WsHeader h = {WS_MAGIC, arch, precision, chunk, (uint64_t)need};
@@ -796,6 +774,29 @@ extern "C" int gd_conv_fft(const float* x, const float* psf, float* out, int adj
     GD_CUDA_CHECK(cudaGetDevice(&dev));
     GD_TRY(init_once(dev));
     return launch_conv_fft(x, psf, out, adjoint, batch, (cudaStream_t)stream);
+}
+
+extern "C" int gd_psf_to_otf(const float* ker, int ker_batch, int kh, int kw, float* psf_out, float* otf_out, int batch, void* stream) {
+    if (batch < 0 || (batch && (!ker || !psf_out || !otf_out))) GD_FAIL(GD_EBADSHAPE, "gd_psf_to_otf: bad batch or NULL buffers");
+    if (kh < 1 || kw < 1 || kh > STAMP || kw > STAMP) GD_FAIL(GD_EBADSHAPE, "gd_psf_to_otf: kernel %dx%d does not fit a 48x48 stamp", kh, kw);
+    if (ker_batch != 1 && ker_batch != batch) GD_FAIL(GD_EBADSHAPE, "gd_psf_to_otf: kernel batch %d must be 1 or %d", ker_batch, batch);
+    // the reference's slice assignments only broadcast a source dimension of 1 or `centre` (anything else raises in torch)
+    const int ce = (kh + 1) / 2;
+    if ((kh - ce != 1 && kh - ce != ce) || (kw - ce != 1 && kw - ce != ce) || 2 * ce > STAMP)
+        GD_FAIL(GD_EBADSHAPE, "gd_psf_to_otf: a %dx%d kernel cannot be broadcast by the reference's quadrant assignment", kh, kw);
+    int dev;
+    GD_CUDA_CHECK(cudaGetDevice(&dev));
+    GD_TRY(init_once(dev));
+    return launch_psf_to_otf(ker, ker_batch, kh, kw, psf_out, reinterpret_cast<float2*>(otf_out), batch, (cudaStream_t)stream);
+}
+
+extern "C" int gd_conv_otf(const float* otf, int otf_batch, const float* x, float* out, int batch, void* stream) {
+    if (batch < 0 || (batch && (!otf || !x || !out))) GD_FAIL(GD_EBADSHAPE, "gd_conv_otf: bad batch or NULL buffers");
+    if (otf_batch != 1 && otf_batch != batch) GD_FAIL(GD_EBADSHAPE, "gd_conv_otf: OTF batch %d must be 1 or %d", otf_batch, batch);
+    int dev;
+    GD_CUDA_CHECK(cudaGetDevice(&dev));
+    GD_TRY(init_once(dev));
+    return launch_conv_otf(reinterpret_cast<const float2*>(otf), otf_batch, x, out, batch, (cudaStream_t)stream);
 }
 
 extern "C" int gd_moments_e(const float* img, float* e12, int batch, void* stream) {

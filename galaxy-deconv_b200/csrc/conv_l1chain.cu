@@ -12,20 +12,20 @@
 //     below the stamp and absorb the tap shifts of the first / last tile;
 //   * the fp32 residual stream lives in TENSOR MEMORY (10 tiles x 32 columns): the second conv of a block adds its
 //     accumulator to it in the epilogue (tcgen05.ld + tcgen05.st), nothing is rounded to fp16 on the residual path;
-//   * conv accumulators: 2 stages x 3 tiles x 32 TMEM columns: a unit of 3 tiles is issued tap by tap (three independent
-//     accumulator chains keep the tensor pipe full) and its epilogue overlaps the MMAs of the next unit;
+//   * conv accumulators: 2 stages x 3 tiles x 32 TMEM columns: the three tiles of a unit are issued by three warps in parallel
+//     and the epilogue of a unit overlaps the MMAs of the next one;
 //   * weights (18 KB per conv) stream through two shared-memory slots, one layer ahead.
 // The halo is RECOMPUTED (layer l of a top item is valid on rows y < 27 - l, mirrored for bottom items): 41 tiles of MMA work per
 // item for 36.75 tiles of output, no inter-CTA exchange.  Tiles are 128 consecutive padded-linear rows; a tile of layer l+1
 // is issued as soon as the epilogues of the layer-l tiles under its 3x3 footprint have arrived (per-tile mbarriers), so the
 // tensor pipe never drains at a layer boundary.
 //
-// Warp roles (448 threads, one persistent CTA per SM):
+// Warp roles (512 threads, one persistent CTA per SM):
 //   warp 0      producer: weight slots; UP: the item's hi -> X and lo -> T windows; DOWN: 29 rows of t (bulk async copies)
-//   warp 1      TMEM allocator + MMA issuer (one elected lane, straight-line 54 MMAs per 3-tile unit)
-//   warps 2-5   helpers (one per TMEM lane quarter): DOWN: x1 = m_head(t) in fp32 on CUDA cores -> X (fp16) + stream (TMEM);
+//   warps 1-3   MMA issuers, warp 1 + j owns tile j of every 3-tile unit (one elected lane each, straight-line 18 MMAs); warp 1 allocates TMEM
+//   warps 4-7   helpers (one per TMEM lane quarter): DOWN: x1 = m_head(t) in fp32 on CUDA cores -> X (fp16) + stream (TMEM);
 //               UP: stream = hi + lo
-//   warps 6-13  epilogue: two groups of four (one warp per lane quarter), alternating units
+//   warps 8-15  epilogue: two groups of four (one warp per lane quarter), alternating units
 #include "conv_epilogue.cuh"
 #include "kernels.cuh"
 #include "launch.cuh"
@@ -50,9 +50,9 @@ constexpr int LC_SMEM = LC_ACT_BYTES + 2 * LC_W_BYTES + 5632;   // 226,176
 constexpr int LC_BOT_Y0 = 20;                        // first image row of a bottom item's window
 constexpr int LC_BOT = LC_ROWS - 10 * MTILE;         // 92: first row of the 10-tile grid of a bottom item
 constexpr int LC_OWN = 24 * LC_WP;                   // 1176 rows of final output per item
-constexpr int LC_THREADS = 14 * 32;
+constexpr int LC_THREADS = (1 + 3 + 4 + 8) * 32;      // producer, LC_J MMA warps, 4 helpers, 8 epilogue warps
 constexpr int LC_STREAM_TILES = 10;
-constexpr int LC_J = 3;                              // tiles per MMA unit: their MMAs are interleaved tap by tap (independent accumulator chains)
+constexpr int LC_J = 3;                              // tiles per MMA unit = MMA-issuing warps
 constexpr int LC_ACC_COL = LC_STREAM_TILES * LC_C;   // 320: two accumulator stages of LC_J x 32 columns follow the stream (512 in all)
 constexpr int LC_HEAD_TILES = 11;
 
@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar(LCB_W_FULL + s), 1); mbar_init(bar(LCB_W_EMPTY + s), 1);
-            mbar_init(bar(LCB_ACC_FULL + s), 1); mbar_init(bar(LCB_ACC_EMPTY + s), 4);
+            mbar_init(bar(LCB_W_FULL + s), 1); mbar_init(bar(LCB_W_EMPTY + s), LC_J);
+            mbar_init(bar(LCB_ACC_FULL + s), LC_J); mbar_init(bar(LCB_ACC_EMPTY + s), 4);
         }
-        mbar_init(bar(LCB_X_FULL), 1); mbar_init(bar(LCB_T_FULL), 1); mbar_init(bar(LCB_X_FREE), 1); mbar_init(bar(LCB_T_FREE), 1);
+        mbar_init(bar(LCB_X_FULL), 1); mbar_init(bar(LCB_T_FULL), 1); mbar_init(bar(LCB_X_FREE), LC_J); mbar_init(bar(LCB_T_FREE), LC_J);
         mbar_init(bar(LCB_ITEM_DONE), 8);
         for (int j = 0; j < LC_HEAD_TILES; ++j) mbar_init(bar(LCB_X_READY + j), 4);
         for (int j = 0; j < 33; ++j) mbar_init(bar(LCB_TILE_DONE + j), 4);
@@ -177,13 +177,16 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
                 load_w(k, 1); load_w(k, 2); load_w(k, 3);
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
+    } else if (warp <= LC_J) {
+        // ===== MMA issuers: warp 1 + jw owns tile jw of every unit (its own 32 accumulator columns of the stage).  Three warps,
+        // because one thread sustains only about one tcgen05.mma per ~57 cycles (measured: a single issuing warp held this kernel
+        // at 27 % tensor-pipe activity whatever the issue order) while an M128 N32 K16 MMA occupies the pipe for ~41. =====
+        const int jw = warp - 1;
         const uint32_t idesc = instr_desc_f16(MTILE, LC_C);
         const uint64_t a_desc0 = smem_desc(smem_u32(smem), LC_PSTRIDE * 16, 128);
         const uint64_t w_desc0 = smem_desc(smem_u32(w_smem), LC_C * 16, 128);
         constexpr uint32_t A_KK = 2 * LC_PSTRIDE, W_KK = 2 * LC_C, W_TAP = 4 * LC_C;   // in 16-byte units
-        uint32_t g = 0;                                   // running tile counter of this CTA (accumulator stage = g & 1)
+        uint32_t g = 0;                                   // running unit counter of this CTA (accumulator stage = g & 1)
         for (int k = 0; k < n_my; ++k) {
             const int it = (int)blockIdx.x + k * (int)gridDim.x, h = it & 1;
             const uint32_t kp = (uint32_t)(k & 1);
@@ -194,47 +197,38 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
                 const int src_pl = (L & 1) ? 4 : 0;       // conv 1 of a block reads X, conv 2 reads T
                 int pw = 0;
                 if (MODE == 1 && L == 0) mbar_wait(bar(LCB_X_FULL), kp);
-                for (int u0 = 0; u0 < n; u0 += LC_J) {
-                    const int nj = n - u0 < LC_J ? n - u0 : LC_J;
-                    int rj[LC_J];
-#pragma unroll
-                    for (int j = 0; j < LC_J; ++j) rj[j] = lc_tile_start(L, h, u0 + (j < nj ? j : nj - 1));
-                    // rows [r - 50, r + 178) of the input of every tile of the unit must be complete
-                    if (!(MODE == 1 && L == 0)) {
-                        while (pw < nprev && (L == 0 ? lc_head_start(h, pw) : lc_tile_start(L - 1, h, pw)) < rj[nj - 1] + MTILE + LC_WP + 1) {
+                for (int u0 = 0; u0 < n; u0 += LC_J, ++g) {
+                    const int i = u0 + jw;
+                    const bool active = i < n;
+                    const int r = active ? lc_tile_start(L, h, i) : 0;
+                    // rows [r - 50, r + 178) of the input of the tile must be complete
+                    if (active && !(MODE == 1 && L == 0)) {
+                        while (pw < nprev && (L == 0 ? lc_head_start(h, pw) : lc_tile_start(L - 1, h, pw)) < r + MTILE + LC_WP + 1) {
                             mbar_wait(bar(L == 0 ? LCB_X_READY + pw : LCB_TILE_DONE + (L - 1) * 11 + pw), kp);
                             ++pw;
                         }
                     }
                     const uint32_t b = g & 1;
-                    mbar_wait(bar(LCB_ACC_EMPTY + b), ((g >> 1) & 1) ^ 1);
+                    mbar_wait(bar(LCB_ACC_EMPTY + b), ((g >> 1) & 1) ^ 1);     // also orders an inactive warp's arrival behind the stage's previous phase
                     tc_fence_after();
-                    const uint32_t d0 = tmem + (uint32_t)(LC_ACC_COL + b * (LC_J * LC_C));
-                    const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(src_pl * LC_PSTRIDE + LC_GAP);
-                    const uint64_t wd = w_desc0 + (uint64_t)((uint32_t)slot * (LC_W_BYTES >> 4));
                     if (elect_one()) {
-                        // tap-major over the tiles of the unit: consecutive MMAs go to different accumulators, so the tensor pipe
-                        // overlaps them (measured: 18 back-to-back MMAs into ONE accumulator run at ~70 instead of ~41 cycles each, and so does the
-                        // second K16 step of a tap when it directly follows the first)
+                        if (active) {
+                            const uint32_t d = tmem + (uint32_t)(LC_ACC_COL + b * (LC_J * LC_C) + jw * LC_C);
+                            const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(src_pl * LC_PSTRIDE + LC_GAP + r);
+                            const uint64_t wd = w_desc0 + (uint64_t)((uint32_t)slot * (LC_W_BYTES >> 4));
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-#pragma unroll
-                            for (int kk = 0; kk < 2; ++kk) {             // K = 32 channels = two K16 steps (chunk planes 2 kk, 2 kk + 1)
-                                const uint64_t bt = wd + (uint64_t)(tap * W_TAP + kk * W_KK);
-#pragma unroll
-                                for (int j = 0; j < LC_J; ++j) {         // innermost: back-to-back MMAs never share an accumulator
-                                    if (j < nj) {
-                                        const uint32_t d = d0 + (uint32_t)(j * LC_C);
-                                        const uint64_t at = ad + (uint64_t)(int64_t)(rj[j] + (tap / 3 - 1) * LC_WP + (tap % 3 - 1) + kk * (int)A_KK);
-                                        if (tap == 0 && kk == 0) tc_mma_f16(d, at, bt, idesc, 0u); else tc_mma_f16_acc(d, at, bt, idesc);
-                                    }
-                                }
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint64_t at = ad + (uint64_t)(int64_t)((tap / 3 - 1) * LC_WP + (tap % 3 - 1));
+                                const uint64_t bt = wd + (uint64_t)(tap * W_TAP);
+                                if (tap == 0) tc_mma_f16(d, at, bt, idesc, 0u); else tc_mma_f16_acc(d, at, bt, idesc);
+                                tc_mma_f16_acc(d, at + A_KK, bt + W_KK, idesc);
                             }
+                            tc_commit(bar(LCB_ACC_FULL + b));
+                        } else {
+                            mbar_arrive(bar(LCB_ACC_FULL + b));
                         }
-                        tc_commit(bar(LCB_ACC_FULL + b));
                     }
                     __syncwarp();
-                    ++g;
                 }
                 if (elect_one()) {
                     tc_commit(bar(LCB_W_EMPTY + slot));
@@ -244,7 +238,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
                 __syncwarp();
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < LC_J + 5) {
         // ===== helpers =====
         // DOWN, phase A (as soon as the previous item's last reads of X are done, i.e. during its 4th conv): x1 = m_head(t) -> X (fp16);
         //       phase B (once the previous item's stream has been consumed): the same fp32 values -> stream (TMEM).  Recomputing the
@@ -335,7 +329,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
         }
     } else {
         // ===== epilogue: group (warps 6-9 / 10-13) takes every second UNIT of the CTA-wide sequence; a warp walks the unit's tiles =====
-        const int q = warp & 3, grp = (warp - 6) >> 2;
+        const int q = warp & 3, grp = (warp - (LC_J + 5)) >> 2;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         uint32_t g = 0;
         for (int k = 0; k < n_my; ++k) {

@@ -12,12 +12,16 @@
 // which is byte-for-byte the global layout of activations ([C/8][Ptot][8]) and packed weights
 // ([tap][K/8][N][8]), so staging is plain 1-D cp.async.bulk (UBLKCP) with mbarrier complete_tx.
 //
-// Warp roles (320 threads, one persistent CTA per SM): warp 0 = bulk-copy producer, warp 1 = TMEM allocator +
-// single-thread MMA issuer, warps 2..9 = epilogue (tcgen05.ld 32x32b -> fused ReLU / residual / skip / fp16 copy /
-// space-to-depth / pixel-shuffle scatter, conv_epilogue.cuh; residual loads are issued before the accumulator wait).
+// Warp roles (416 threads, one persistent CTA per SM): warp 0 = bulk-copy producer; warps 1..4 = MMA issue, warp 1+j owns
+// tile j of every item (warp 1 also allocates TMEM).  Several issuing warps are needed: ONE thread sustains only about one
+// tcgen05.mma per ~57 cycles whatever the issue order (measured in round 2: a single warp issuing all J tiles interleaved
+// lowered the N = 64 layers from 57 % to 45 % tensor-pipe activity, profiles/README_r02.md), below the 41..49-cycle MMAs of the
+// narrow layers.  Warps 5..12 = epilogue (tcgen05.ld 32x32b -> fused ReLU / residual / skip / fp16 hi-lo stream /
+// space-to-depth / pixel-shuffle scatter, conv_epilogue.cuh; residual loads are issued one item ahead).
 // The 512 TMEM columns hold two accumulator stages, so the epilogue of work item i overlaps the MMAs of item i+1.
 // Layers whose packed weights fit (<= 96 KB: levels 1-2 of the U-Net and all k2s2 layers) keep them resident in
-// shared memory for the whole kernel; larger layers stream (slab, tap) weight stages through a 6-deep ring.
+// shared memory for the whole kernel; larger layers stream (slab, tap) weight stages through a 6-deep ring shared by a
+// cluster of 4 CTAs (multicast bulk copies + multicast tcgen05.commit).
 #include "conv_epilogue.cuh"
 #include "kernels.cuh"
 #include "launch.cuh"
@@ -45,8 +49,6 @@ struct UmmaCfg {
     int items_m;     // ceil(tiles / J)
     int nsl_log2, nb32_log2;   // log2(nslices), log2(ncta / 32): both are powers of two
     int abl;         // diagnostic ablation bits (GDECONV_ABL): 1 = no weight streaming, 2 = no epilogue global traffic, 4 = no activation loads
-    int l2pf;        // producer prefetches the residual / skip rows of each item into L2
-    int res_nc;      // hi/lo residual prefetch through ld.global.nc (1) or plain ld.global (0)
     int late_pf;     // epilogue: all residual loads of the next item are issued after this item's last register use
     int cls;         // CTAs per cluster sharing every streamed weight stage by multicast (1 = no cluster)
     int aux_off;     // mode 1: byte offset of the 8 warp-private 4 KB transpose stages of epi_up_unit in dynamic shared memory
@@ -145,14 +147,6 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                 const int im = item_m(item), ns = item & (c.nslices - 1);
                 const bool dummy = im >= c.items_m;
                 const size_t row0 = (size_t)p.g.base0 + (size_t)im * J * MTILE - c.halo;
-                if (c.l2pf && p.mode == 0 && (p.res32 || p.skip32) && !dummy) {
-                    // the epilogue of this item will read its residual / skip rows: pull them from HBM into L2 now
-                    const size_t r0 = (size_t)p.g.base0 + (size_t)im * J * MTILE;
-                    for (int pl = ns * (c.ncta / 4); pl < (ns + 1) * (c.ncta / 4); ++pl) {
-                        if (p.res32) bulk_prefetch_l2(p.res32 + ((size_t)pl * p.g.Ptot + r0) * 4, (uint32_t)(J * MTILE * 16));
-                        if (p.skip32) bulk_prefetch_l2(p.skip32 + ((size_t)pl * p.g.Ptot + r0) * 4, (uint32_t)(J * MTILE * 16));
-                    }
-                }
                 for (int s = 0; s < nslabs; ++s) {
                     mbar_wait(a_empty(as), aph ^ 1);
                     if (((c.abl & 4) && aph) || dummy) {
@@ -273,9 +267,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
                     const uint4* sl = reinterpret_cast<const uint4*>(p.res_lo) + o;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        uint4 t, u;
-                        if (c.res_nc) { t = __ldg(sh + (size_t)k * Ptot); u = __ldg(sl + (size_t)k * Ptot); }
-                        else { t = sh[(size_t)k * Ptot]; u = sl[(size_t)k * Ptot]; }
+                        const uint4 t = __ldg(sh + (size_t)k * Ptot), u = __ldg(sl + (size_t)k * Ptot);
                         d[4 * k] = __uint_as_float(t.x); d[4 * k + 1] = __uint_as_float(t.y); d[4 * k + 2] = __uint_as_float(t.z); d[4 * k + 3] = __uint_as_float(t.w);
                         d[16 + 4 * k] = __uint_as_float(u.x); d[17 + 4 * k] = __uint_as_float(u.y); d[18 + 4 * k] = __uint_as_float(u.z); d[19 + 4 * k] = __uint_as_float(u.w);
                     }
@@ -440,15 +432,11 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_conv_umma(const ConvParams 
 
 static int g_num_sms = 0;
 static int g_cluster = 4;
-static int g_res_nc = 1;
 static int g_late_pf = -1;     // request the next item's residual after the LAST unit of this item (1) or after each unit (0);
                                // -1 (default): late for the streamed-weight layers (levels 3-4: 327 -> 297 us, 456 -> 396 us), early for
                                // the resident ones (level 1 tail conv: 708 vs 794 us), GDECONV_LATEPF overrides
-static int g_jcols = 128;      // accumulator columns per item of the resident-weight 3x3 layers
-static int g_jcols1 = 128;     // ... of the 1-tap (k2s2) layers
-static int g_l2pf = 0;
 static int g_bstages = 6;
-static int g_astages = 4;
+constexpr int A_STAGES = 4;    // A ring depth: deeper rings measured slower everywhere (profiles/README_r01.md)
 static int g_abl = 0;
 
 // Optional per-launch timing of k_conv_umma with CUDA events on the launching stream (gd_profile_begin/end):
@@ -496,14 +484,9 @@ int conv_umma_init() {
     int dev;
     GD_CUDA_CHECK(cudaGetDevice(&dev));
     GD_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    if (const char* e = getenv("GDECONV_L2PF")) g_l2pf = atoi(e);
     if (const char* e = getenv("GDECONV_ABL")) g_abl = atoi(e);
     if (const char* e = getenv("GDECONV_LATEPF")) g_late_pf = atoi(e);
-    if (const char* e = getenv("GDECONV_RESNC")) g_res_nc = atoi(e) != 0;
-    if (const char* e = getenv("GDECONV_JCOLS")) { g_jcols = atoi(e) == 256 ? 256 : 128; }
-    if (const char* e = getenv("GDECONV_JCOLS1")) { g_jcols1 = atoi(e) == 256 ? 256 : 128; }
     if (const char* e = getenv("GDECONV_CLUSTER")) { g_cluster = atoi(e); if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4) g_cluster = 4; }
-    if (const char* e = getenv("GDECONV_ASTAGES")) { g_astages = atoi(e); if (g_astages < 2 || g_astages > MAX_A_STAGES) g_astages = 4; }
     if (const char* e = getenv("GDECONV_BSTAGES")) { g_bstages = atoi(e); if (g_bstages < 2 || g_bstages > MAX_B_STAGES) g_bstages = 6; }
 #define GD_UMMA_ATTR(J, KK)                                                                                                        \
     GD_CUDA_CHECK(cudaFuncSetAttribute(k_conv_umma<J, KK, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX)); \
@@ -540,7 +523,7 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
     }
     // resident weights: <= 128 accumulator columns per item (2 epilogue units per warp, fine-grained A ring, good tail
     // balance); streamed weights: 256 columns so that every weight stage is reused by twice as many rows
-    c.J = (c.b_resident ? (p.ntaps == 1 ? g_jcols1 : g_jcols) : ACC_STAGE_COLS) / c.ncta;
+    c.J = (c.b_resident ? 128 : ACC_STAGE_COLS) / c.ncta;
     if (c.J > 4) c.J = 4;
     for (;; c.J >>= 1) {
         c.win_rows = MTILE * c.J + 2 * c.halo;
@@ -548,17 +531,15 @@ static int make_cfg(const ConvParams& p, UmmaCfg* out) {
         if (b_region + 2 * (size_t)c.a_stage_bytes <= UMMA_SMEM_MAX || c.J == 1) break;
     }
     c.a_stages = (int)((UMMA_SMEM_MAX - b_region) / c.a_stage_bytes);
-    if (c.a_stages > g_astages) c.a_stages = g_astages;
+    if (c.a_stages > A_STAGES) c.a_stages = A_STAGES;
     if (c.a_stages < 2) { set_error("conv_umma: layer does not fit shared memory"); return GD_EUNSUPPORTED; }
     c.smem = (size_t)c.a_stages * c.a_stage_bytes + b_region;
     if (p.mode == 1) c.aux_off += c.a_stages * c.a_stage_bytes;     // relative to the start of dynamic smem
     const int tiles = (p.g.M + MTILE - 1) / MTILE;
     c.items_m = (tiles + c.J - 1) / c.J;
-    c.l2pf = g_l2pf;
     c.abl = g_abl;
     c.cls = (!c.b_resident && (c.BK / 8) % g_cluster == 0) ? g_cluster : 1;
     c.late_pf = g_late_pf < 0 ? !c.b_resident : g_late_pf != 0;
-    c.res_nc = g_res_nc;
     auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
     c.nsl_log2 = ilog2(c.nslices); c.nb32_log2 = ilog2(c.ncta / 32);
     if ((1 << c.nsl_log2) != c.nslices || (1 << c.nb32_log2) != c.ncta / 32) { set_error("conv_umma: N=%d must split into power-of-two slices", p.N); return GD_EUNSUPPORTED; }

@@ -355,6 +355,71 @@ __global__ void __launch_bounds__(U_THREADS) k_conv_fft(const float* __restrict_
     }
 }
 
+// psf_to_otf(ker, size) with the reference's signature and semantics (utils/utils_torch.py:79-92) for size = (B,1,48,48):
+// `psf` = zeros(size) with the four quadrant assignments (centre = (kh + 1) / 2 for BOTH axes, each source block broadcast
+// to centre x centre the way torch broadcasts a size-1 dimension, later assignments overwriting earlier ones -- for a 3x3 kernel
+// this leaves the 7-non-zero array of SURVEY.md section 0.6), `otf` = fft2(psf) as the FULL 48x48 complex spectrum.
+// kb = 1: one kernel shared by the batch (the reference's broadcasting assignment), kb = batch: one kernel per stamp.
+__global__ void __launch_bounds__(U_THREADS) k_psf_to_otf(const float* __restrict__ ker, int kb, int kh, int kw, float* __restrict__ psf_out,
+                                                          float2* __restrict__ otf_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Z = reinterpret_cast<float2*>(smem_raw);
+    float2* S = Z + ZU;
+    float2* tw = S + 2 * SU;
+    const int b = blockIdx.x;
+    const float* kp = ker + (kb == 1 ? 0 : (size_t)b * kh * kw);
+    const int ce = (kh + 1) / 2;
+    fill_twiddles<48>(tw);
+    for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+        const int r = i / 48, c = i - r * 48;
+        const bool top = r < ce, bot = r >= 48 - ce, left = c < ce, right = c >= 48 - ce;
+        float v = 0.f;
+        // source block (rows r0.., cols c0.., shape sh x sw) of the LAST assignment that covers (r, c)
+        int r0 = -1, c0 = 0, sh = 0, sw = 0, ri = 0, ci = 0;
+        if (bot && right) { r0 = 0; c0 = 0; sh = ce; sw = ce; ri = r - (48 - ce); ci = c - (48 - ce); }
+        else if (bot && left) { r0 = 0; c0 = ce; sh = ce; sw = kw - ce; ri = r - (48 - ce); ci = c; }
+        else if (top && right) { r0 = ce; c0 = 0; sh = kh - ce; sw = ce; ri = r; ci = c - (48 - ce); }
+        else if (top && left) { r0 = ce; c0 = ce; sh = kh - ce; sw = kw - ce; ri = r; ci = c; }
+        if (r0 >= 0) v = kp[(r0 + (sh == 1 ? 0 : ri)) * kw + c0 + (sw == 1 ? 0 : ci)];
+        psf_out[(size_t)b * NPIX + i] = v;
+        zpix<48>(Z, r, c) = v;
+    }
+    fwd2d<FU48, SPU>(Z, S, tw);
+    float2* ob = otf_out + (size_t)b * NPIX;
+    for (int q = threadIdx.x; q < FU_SPEC; q += blockDim.x) {
+        const int s1 = q / FU_NH, k2 = q - s1 * FU_NH, k1 = FU48::L::freq(s1);
+        const float2 h = S[s1 * SPU + k2];
+        ob[k1 * 48 + k2] = h;
+        if (k2 > 0 && k2 < 24) ob[((48 - k1) % 48) * 48 + (48 - k2)] = cconj(h);      // Hermitian half the transform does not store
+    }
+}
+
+// conv_fft_batch(H, x) with the reference's signature (utils/utils_torch.py:46-50): ifft2(fft2(x) * H).real for a FULL
+// complex spectrum H [B][48][48].  x is real, so the real part of the inverse transform only sees the Hermitian part of H,
+// Hs(k) = (H(k) + conj(H(-k))) / 2, which is what the half-spectrum transform multiplies by (exact for any H).
+__global__ void __launch_bounds__(U_THREADS) k_conv_otf(const float2* __restrict__ H, int hb, const float* __restrict__ x, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Z = reinterpret_cast<float2*>(smem_raw);
+    float2* S = Z + ZU;
+    float2* tw = S + 2 * SU;
+    const size_t o = (size_t)blockIdx.x * NPIX;
+    const float2* Hb = H + (hb == 1 ? 0 : o);
+    fill_twiddles<48>(tw);
+    load_packed48(Z, x + o, 1.f, false);
+    fwd2d<FU48, SPU>(Z, S, tw);
+    for (int q = threadIdx.x; q < FU_SPEC; q += blockDim.x) {
+        const int s1 = q / FU_NH, k2 = q - s1 * FU_NH, k1 = FU48::L::freq(s1);
+        const float2 a = Hb[k1 * 48 + k2], bq = Hb[((48 - k1) % 48) * 48 + (48 - k2) % 48];
+        const float2 hs = make_float2(0.5f * (a.x + bq.x), 0.5f * (a.y - bq.y));
+        S[s1 * SPU + k2] = cmul(S[s1 * SPU + k2], hs);
+    }
+    inv2d<FU48, SPU>(S, Z, tw);
+    for (int i = threadIdx.x; i < NPIX; i += blockDim.x) {
+        int r = i / 48, c = i - r * 48;
+        out[o + i] = zpix<48>(Z, r, c) * (1.0f / 2304.f);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Path U.  Per-stamp state in the workspace: H (half spectrum, with the (-1)^k sign), x, z(=denoiser out),
 // v, u1, u2, Hx.  The reference's three conv_fft_batch calls per iteration (:207,:209,:213) collapse to
@@ -575,6 +640,8 @@ int fft_kernels_init() {
     if ((rc = opt_in_smem(k_g_xupdate<true>, G_SMEM_XUP))) return rc;
     if ((rc = opt_in_smem(k_solver, SOLVER_SMEM))) return rc;
     if ((rc = opt_in_smem(k_conv_fft, SOLVER_SMEM))) return rc;
+    if ((rc = opt_in_smem(k_psf_to_otf, SOLVER_SMEM_LIGHT))) return rc;
+    if ((rc = opt_in_smem(k_conv_otf, SOLVER_SMEM_LIGHT))) return rc;
     if ((rc = opt_in_smem(k_u_prologue, U_SMEM))) return rc;
     if ((rc = opt_in_smem(k_u_post, U_SMEM))) return rc;
     return GD_OK;
@@ -636,6 +703,18 @@ int launch_solver(int kind, int n_iters, float lam, const float* y, const float*
 int launch_conv_fft(const float* x, const float* psf, float* out, int adjoint, int batch, cudaStream_t st) {
     if (batch <= 0) return GD_OK;
     k_conv_fft<<<batch, U_THREADS, SOLVER_SMEM_LIGHT, st>>>(x, psf, out, adjoint);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_psf_to_otf(const float* ker, int kb, int kh, int kw, float* psf_out, float2* otf_out, int batch, cudaStream_t st) {
+    if (batch <= 0) return GD_OK;
+    k_psf_to_otf<<<batch, U_THREADS, SOLVER_SMEM_LIGHT, st>>>(ker, kb, kh, kw, psf_out, otf_out);
+    GD_LAUNCHED();
+    return GD_OK;
+}
+int launch_conv_otf(const float2* H, int hb, const float* x, float* out, int batch, cudaStream_t st) {
+    if (batch <= 0) return GD_OK;
+    k_conv_otf<<<batch, U_THREADS, SOLVER_SMEM_LIGHT, st>>>(H, hb, x, out);
     GD_LAUNCHED();
     return GD_OK;
 }

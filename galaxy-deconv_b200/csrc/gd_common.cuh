@@ -44,7 +44,10 @@ struct Geom {
 
 // Exact unsigned division of n < 2^26 by an invariant d through one 32x32->64 multiply (Granlund-Montgomery):
 // with l = ceil(log2 d), shift = 26 + l and magic = ceil(2^shift / d) < 2^27, n * (magic*d - 2^shift) < 2^shift holds
-// for every n < 2^26.  GEMM rows of a chunk stay far below 2^26 (make_geom checks).
+// for every n < 2^26.  geom_rows_ok() is the gate: gd_workspace_bytes / gd_workspace_init reject a chunk whose GEMM rows (plus the
+// tile and halo slack the kernels add) reach 2^26, gd_max_chunk() reports the largest admitted chunk, and
+// tests/test_abi.py checks div_by_magic exhaustively over [0, 2^26) for every divisor the geometry uses.
+constexpr uint32_t DIV_MAGIC_LIMIT = 1u << 26;
 inline void div_magic(uint32_t d, uint32_t* magic, uint32_t* shift) {
     uint32_t l = 0;
     while ((1u << l) < d) ++l;
@@ -65,6 +68,13 @@ inline Geom make_geom(int H, int batch) {
     // (conv_rb.cu: the x window of the last 384-row item ends up to 498 rows past M)
     g.Ptot = mt * MTILE + 2 * g.base0 + 5 * MTILE;
     return g;
+}
+
+// every row index a kernel may decode for a chunk of `batch` stamps at resolution H stays below the div_by_magic limit
+inline bool geom_rows_ok(int H, long long batch) {
+    const long long S = (long long)(H + 1) * (H + 1), M = batch * S;
+    const long long mt = ((M + MTILE - 1) / MTILE + 7) / 8 * 8;
+    return mt * MTILE + 2 * (H + 2 + 64) + 5 * MTILE < (long long)DIV_MAGIC_LIMIT;
 }
 
 GD_HD bool row_valid(int m, int S, int Wp, int H, int W, int M) {

@@ -9,9 +9,6 @@ namespace gd {
 int fft_kernels_init();
 int subnet_init();
 int conv_umma_init();
-int conv_chain_init();
-size_t chain_flag_words(int max_rows);
-int launch_conv_chain(const ConvParams* layers, int nl, unsigned int* flags, cudaStream_t st);
 void conv_profile_begin();
 int conv_profile_end(double* ms_total, double* flops_total, unsigned long long* launches);
 int conv_profile_mark(double flops, cudaStream_t st, cudaEvent_t* stop);
@@ -36,6 +33,8 @@ int launch_fill_rho(const float* src, int n_rho, float* rho, int batch, cudaStre
 int launch_solver(int kind, int n_iters, float lam, const float* y, const float* psf, const float* alpha, float* out,
                   int batch, cudaStream_t st);
 int launch_conv_fft(const float* x, const float* psf, float* out, int adjoint, int batch, cudaStream_t st);
+int launch_psf_to_otf(const float* ker, int kb, int kh, int kw, float* psf_out, float2* otf_out, int batch, cudaStream_t st);
+int launch_conv_otf(const float2* H, int hb, const float* x, float* out, int batch, cudaStream_t st);
 int launch_u_prologue(const float* y, const float* psf, const float* alpha, int v0_over_alpha, float2* Hw, float* x,
                       float* z, float* v, float* u1, float* u2, float* Hx, int batch, cudaStream_t st);
 int launch_u_pre(int llh, const float* y, const float* alpha, const float* rho, int n_rho, int n, int it, const float* x,

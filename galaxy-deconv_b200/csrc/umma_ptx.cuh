@@ -1,4 +1,4 @@
-// PTX wrappers shared by the tcgen05 kernels (conv_umma.cu, conv_chain.cu): mbarrier, bulk-async copies (TMA engine),
+// PTX wrappers shared by the tcgen05 kernels (conv_umma.cu, conv_rb.cu, conv_l1chain.cu): mbarrier, bulk-async copies (TMA engine),
 // tcgen05.mma / commit / ld, shared-memory matrix descriptors.
 #pragma once
 #include <cuda_runtime.h>
@@ -8,13 +8,13 @@
 
 namespace gd {
 
-// ---- kernel shape constants shared by conv_umma.cu and conv_chain.cu ----
+// ---- kernel shape constants shared by conv_umma.cu and conv_rb.cu ----
 enum { EPI_PLAIN = 0, EPI_FULL = 1, EPI_HT = 2 };   // EPI_HT = EPI_FULL + head recompute / tail partial sums (level 0)
 constexpr int EPI_WARPS = 8;
 constexpr int MMA_WARPS = 4;                        // warps 1..4: MMA issuers, one 128-row tile of the item each (J <= 4)
 constexpr int EPI_WARP0 = 1 + MMA_WARPS;            // warps 5..12: epilogue
 constexpr int UMMA_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
-constexpr int MAX_A_STAGES = 12;                    // upper bound; the default ring depth is 4 (GDECONV_ASTAGES): deeper rings measured slower
+constexpr int MAX_A_STAGES = 4;                     // A ring depth (deeper rings measured slower, profiles/README_r01.md)
 constexpr int MAX_B_STAGES = 8;
 constexpr int TMEM_COLS = 512;                      // one CTA per SM owns all of TMEM: 2 accumulator stages x 256 columns
 constexpr int ACC_STAGE_COLS = 256;

@@ -20,7 +20,7 @@ PRECISIONS = {'fp32_simt': PREC_FP32_SIMT, 'fp16_umma': PREC_FP16_UMMA, 'fp16_si
 SYMBOLS = ('gd_version', 'gd_last_error', 'gd_pack_weights', 'gd_free_weights', 'gd_workspace_bytes', 'gd_workspace_init',
            'gd_admm_forward', 'gd_resunet_forward', 'gd_subnet_forward', 'gd_fft_solver', 'gd_conv_fft', 'gd_moments_e',
            'gd_launch_count', 'gd_debug_geom', 'gd_debug_tapgemm', 'gd_profile_begin', 'gd_profile_end', 'gd_pack_xdense', 'gd_free_xdense', 'gd_xdense_workspace_bytes',
-           'gd_xdense_forward', 'gd_tikhonet_forward')
+           'gd_xdense_forward', 'gd_tikhonet_forward', 'gd_psf_to_otf', 'gd_conv_otf', 'gd_max_chunk', 'gd_debug_divmagic')
 
 
 class GdTensorDesc(C.Structure):
@@ -29,8 +29,14 @@ class GdTensorDesc(C.Structure):
 
 def _load():
     path = _build.LIB
-    if not os.path.exists(path) or (os.environ.get('GDECONV_REBUILD') and not _build.is_current()):
-        _build.build()
+    # A stale binary must never load silently: the .so is git-ignored and survives source updates, and struct layouts / packed
+    # weight layouts can change without any symbol changing.  The source hash is cheap; rebuild on mismatch (nvcc is part of
+    # the image, here and on the GPU box) and fail loudly when that is impossible.
+    if not _build.is_current():
+        try:
+            _build.build()
+        except Exception as e:
+            raise ImportError(f'libgdeconv.so is missing or older than csrc/ and could not be rebuilt with nvcc: {e}') from e
     lib = C.CDLL(path)
     vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
     lib.gd_version.restype = i
@@ -56,12 +62,30 @@ def _load():
     lib.gd_xdense_workspace_bytes.restype = sz
     lib.gd_xdense_forward.argtypes = [vp, vp, vp, i, vp, sz, i, vp]
     lib.gd_tikhonet_forward.argtypes = [vp, i, f, vp, vp, vp, vp, i, vp, sz, i, vp]
+    lib.gd_psf_to_otf.argtypes = [vp, i, i, i, vp, vp, i, vp]
+    lib.gd_conv_otf.argtypes = [vp, i, vp, vp, i, vp]
+    lib.gd_max_chunk.restype = i
+    lib.gd_debug_divmagic.argtypes = [C.c_uint, C.c_uint, C.c_uint]
+    lib.gd_debug_divmagic.restype = C.c_longlong
     lib.gd_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.gd_debug_geom.argtypes = [i, i, C.POINTER(C.c_int * 7)]
     lib.gd_debug_tapgemm.argtypes = [i, i, i, i, i, i, i, vp, vp, vp, vp]
     for name in SYMBOLS:
         getattr(lib, name)          # AttributeError here = the .so does not match the header
+    want = _header_version()
+    if want is not None and lib.gd_version() != want:
+        raise ImportError(f'libgdeconv.so reports version {lib.gd_version()}, include/gdeconv.h declares {want}')
     return lib
+
+
+def _header_version():
+    import re
+    try:
+        text = open(os.path.join(os.path.dirname(_build.PKG), 'include', 'gdeconv.h')).read()
+    except OSError:
+        return None
+    m = re.search(r'#define\s+GD_VERSION\s+(\d+)', text)
+    return int(m.group(1)) if m else None
 
 
 lib = _load()

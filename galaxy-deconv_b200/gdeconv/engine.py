@@ -32,7 +32,10 @@ def max_chunk(arch=_lib.ARCH_G) -> int:
     this path (profiles/ablation_r01.md), so the default is large: 8192 stamps = 22 GB of workspace for path G,
     4096 = 22 GB for the twice-as-wide path U."""
     env = os.environ.get('GDECONV_CHUNK')
-    return int(env) if env else (_DEFAULT_CHUNK if arch == _lib.ARCH_G else _DEFAULT_CHUNK // 2)
+    c = int(env) if env else (_DEFAULT_CHUNK if arch == _lib.ARCH_G else _DEFAULT_CHUNK // 2)
+    # the row decode of the kernels is exact below 2^26 GEMM rows (~27.9 k stamps): larger requests are clamped here and
+    # rejected by gd_workspace_bytes / gd_workspace_init, never mis-decoded
+    return max(1, min(c, int(lib.gd_max_chunk())))
 
 
 def launch_count() -> int:
@@ -239,6 +242,95 @@ class AdmmEngine:
                                           _ptr(rho), _ptr(ana), B, _ptr(ws), nbytes, _stream(dev)))
         return out, rho, ana
 
+    # ---- host-resident batches: chunk-pipelined H2D / compute / D2H ----------------------------------------------------
+    def _host_state(self, dev, prec, cap):
+        key = (dev.index, prec, cap)
+        st = self.__dict__.setdefault('_host', {}).get(key)
+        if st is None:
+            mk = lambda *shape: [torch.empty(*shape, device=dev) for _ in range(2)]
+            st = dict(y=mk(cap, 1, STAMP, STAMP), psf=mk(cap, 1, STAMP, STAMP), a=mk(cap), out=mk(cap, 1, STAMP, STAMP),
+                      h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev),
+                      ev_h2d=[torch.cuda.Event() for _ in range(2)], ev_comp=[torch.cuda.Event() for _ in range(2)],
+                      ev_d2h=[torch.cuda.Event() for _ in range(2)])
+            self._host.clear()                      # one staging set per engine
+            self._host[key] = st
+        return st
+
+    @staticmethod
+    def _host_plan(B, cap):
+        """Chunk sizes for a host-resident batch: a short first and last chunk (their H2D / D2H cannot hide behind compute of
+        the same call) around balanced large chunks (long persistent kernels)."""
+        edge = min(1024, cap)
+        if B <= 3 * edge:
+            return [B] if B <= cap else [B - B // 2, B // 2]
+        mid = B - 2 * edge
+        n = max(1, -(-mid // cap))
+        per = -(-mid // n)
+        sizes = [edge] + [min(per, mid - i * per) for i in range(n)] + [edge]
+        return [v for v in sizes if v > 0]
+
+    def admm_host(self, y, psf, alpha, out=None, want_e=True, device=None, precision=None):
+        """model(y, psf, alpha) for a batch that lives in (pinned) HOST memory: the batch is cut into chunks and chunk k+1's
+        host->device copies and chunk k-1's device->host copy run on two copy streams while chunk k computes (one
+        cudaMemcpyAsync per tensor and chunk, double-buffered device staging).  Returns (out_host, e12) with out_host the
+        deconvolved stamps in host memory (``out`` if given) and e12 [B,2] the moment ellipticities on the device (or None).
+        Stream-ordered on the current stream: synchronize it before reading out_host."""
+        for name, t in (('y', y), ('psf', psf)):
+            if not torch.is_tensor(t) or t.is_cuda or t.dtype != torch.float32 or t.dim() != 4 or tuple(t.shape[1:]) != (1, STAMP, STAMP):
+                raise ValueError(f'admm_host: {name} must be a float32 host tensor [B,1,{STAMP},{STAMP}]')
+        B = y.shape[0]
+        if psf.shape[0] != B:
+            raise ValueError('admm_host: y and psf differ in batch size')
+        y, psf = y.contiguous(), psf.contiguous()
+        a = alpha.detach().to(torch.float32).reshape(-1)
+        a = (a.expand(B) if a.numel() == 1 and B != 1 else a).contiguous()
+        if a.numel() != B:
+            raise ValueError(f'alpha has {a.numel()} elements for a batch of {B}')
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        precision = precision or default_precision()
+        prec = _lib.PRECISIONS[precision]
+        if out is None:
+            out = torch.empty(B, 1, STAMP, STAMP).pin_memory()
+        with torch.cuda.device(dev):
+            w = self.weights(dev, precision)
+            cap = _chunk_for(B, self.arch)
+            sizes = self._host_plan(B, cap)
+            st = self._host_state(dev, prec, cap)
+            wss = [_workspace(dev, self.arch, prec, cap, slot=s) for s in range(2)]
+            cur = torch.cuda.current_stream(dev)
+            side = _side_stream(dev) if len(sizes) > 1 and n_streams() == 2 else cur
+            if side is not cur:
+                side.wait_stream(cur)
+            e12 = torch.empty(B, 2, device=dev) if want_e else None
+            if e12 is not None and side is not cur:
+                e12.record_stream(side)
+            c0 = 0
+            for i, nb in enumerate(sizes):
+                s = i & 1
+                comp = cur if s == 0 else side
+                with torch.cuda.stream(st['h2d']):
+                    st['h2d'].wait_event(st['ev_comp'][s])           # the slot's previous chunk no longer reads its inputs
+                    st['y'][s][:nb].copy_(y[c0:c0 + nb], non_blocking=True)
+                    st['psf'][s][:nb].copy_(psf[c0:c0 + nb], non_blocking=True)
+                    st['a'][s][:nb].copy_(a[c0:c0 + nb], non_blocking=True)
+                    st['ev_h2d'][s].record(st['h2d'])
+                comp.wait_event(st['ev_h2d'][s])
+                comp.wait_event(st['ev_d2h'][s])                     # the slot's previous result has left the device
+                check(lib.gd_admm_forward(w.handle, _lib.LLH_GAUSSIAN, 0, _ptr(st['y'][s]), _ptr(st['psf'][s]), _ptr(st['a'][s]),
+                                          _ptr(st['out'][s]), None, None, nb, _ptr(wss[s][0]), wss[s][1], C.c_void_p(comp.cuda_stream)))
+                if e12 is not None:
+                    check(lib.gd_moments_e(_ptr(st['out'][s]), _ptr(e12[c0:c0 + nb]), nb, C.c_void_p(comp.cuda_stream)))
+                st['ev_comp'][s].record(comp)
+                with torch.cuda.stream(st['d2h']):
+                    st['d2h'].wait_event(st['ev_comp'][s])
+                    out[c0:c0 + nb].copy_(st['out'][s][:nb], non_blocking=True)
+                    st['ev_d2h'][s].record(st['d2h'])
+                c0 += nb
+            if side is not cur:
+                cur.wait_stream(side)
+            cur.wait_stream(st['d2h'])
+        return out, e12
+
     def resunet(self, x, precision=None):
         x = require_cuda_stamps('x', x)
         dev = x.device
@@ -286,6 +378,40 @@ def conv_fft_batch(x, psf, adjoint=False):
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
         check(lib.gd_conv_fft(_ptr(x), _ptr(psf), _ptr(out), int(bool(adjoint)), x.shape[0], _stream(x.device)))
+    return out
+
+
+def psf_to_otf(ker, size):
+    """psf_to_otf(ker, size) of utils/utils_torch.py:79-92 on the device: (psf, otf) with psf fp32 and otf complex64, both
+    of shape ``size`` = (B,1,48,48); ``ker`` is [1 or B,1,kh,kw] fp32 CUDA."""
+    size = tuple(int(v) for v in size)
+    if len(size) != 4 or size[1] != 1 or size[2] != STAMP or size[3] != STAMP:
+        raise ValueError(f'psf_to_otf: size must be (B,1,{STAMP},{STAMP}), got {size}')
+    if not torch.is_tensor(ker) or not ker.is_cuda:
+        raise RuntimeError('psf_to_otf: the kernel must be a CUDA tensor (gdeconv has no CPU path)')
+    if ker.dtype != torch.float32 or ker.dim() != 4 or ker.shape[1] != 1 or ker.shape[0] not in (1, size[0]):
+        raise ValueError(f'psf_to_otf: kernel must be float32 [1 or {size[0]},1,kh,kw], got {ker.dtype} {tuple(ker.shape)}')
+    ker = ker.detach().contiguous()
+    dev, B = ker.device, size[0]
+    psf = torch.empty(size, device=dev)
+    otf = torch.empty(size + (2,), device=dev)
+    with torch.cuda.device(dev):
+        check(lib.gd_psf_to_otf(_ptr(ker), ker.shape[0], ker.shape[2], ker.shape[3], _ptr(psf), _ptr(otf), B, _stream(dev)))
+    return psf, torch.view_as_complex(otf)
+
+
+def conv_otf(H, x):
+    """conv_fft_batch(H, x) of utils/utils_torch.py:46-50: ifft2(fft2(x) * H).real with a full complex spectrum H [1 or B,1,48,48]."""
+    x = require_cuda_stamps('x', x)
+    B, dev = x.shape[0], x.device
+    if not torch.is_tensor(H) or not H.is_cuda or H.dtype != torch.complex64:
+        raise TypeError('conv_fft_batch: H must be a complex64 CUDA tensor')
+    if H.dim() != 4 or H.shape[1] != 1 or H.shape[2] != STAMP or H.shape[3] != STAMP or H.shape[0] not in (1, B):
+        raise ValueError(f'conv_fft_batch: H must have shape [1 or {B},1,{STAMP},{STAMP}], got {tuple(H.shape)}')
+    Hr = torch.view_as_real(H.detach().resolve_conj().contiguous())
+    out = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        check(lib.gd_conv_otf(_ptr(Hr), H.shape[0], _ptr(x), _ptr(out), B, _stream(dev)))
     return out
 
 

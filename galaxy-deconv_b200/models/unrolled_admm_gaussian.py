@@ -76,3 +76,11 @@ class UnrolledADMMGaussian(nn.Module):
         n = self.n_iters
         return ([ana[i, 0] for i in range(n)], [ana[i, 1] for i in range(n)], [ana[i, 2] for i in range(n)],
                 [rho[:, i].reshape(-1, 1, 1, 1) for i in range(n)])
+
+    def deconvolve_host(self, y, kernel, alpha, out=None, want_e=True, device=None):
+        """forward() for a batch held in (pinned) host memory, e.g. a test.py-style data set loaded once: chunk-pipelined
+        host->device copies, compute and device->host copies (gdeconv.engine.AdmmEngine.admm_host).  Returns
+        (deconvolved stamps in host memory, [B,2] moment ellipticities on the device or None)."""
+        if self.analysis:
+            raise NotImplementedError('deconvolve_host returns the final stamps only (analysis=False)')
+        return self._engine[0].admm_host(y, kernel, alpha, out=out, want_e=want_e, device=device, precision=self.precision)

@@ -108,6 +108,16 @@ GD_API int gd_fft_solver(int kind, int n_iters, float lam, const float* y, const
  * out = ifft2(fft2(x) * H).real, or with conj(H) when `adjoint`.  Used by the parity tests of the FFT core. */
 GD_API int gd_conv_fft(const float* x, const float* psf, float* out, int adjoint, int batch, void* stream);
 
+/* Replaces psf_to_otf(ker, size) (utils/utils_torch.py:79-92) for size = (batch,1,48,48), on the device (the reference builds
+ * `psf` on the CPU and FFTs it there).  ker [ker_batch][kh][kw] fp32 with ker_batch = 1 (broadcast, e.g. the 3x3 Laplacian of
+ * models/Tikhonet.py:26) or = batch; psf_out [batch][48*48] fp32 is the circularly shifted / broadcast kernel, otf_out
+ * [batch][48*48] interleaved complex64 its FULL spectrum.  Kernel sizes torch could not broadcast are GD_EBADSHAPE. */
+GD_API int gd_psf_to_otf(const float* ker, int ker_batch, int kh, int kw, float* psf_out, float* otf_out, int batch, void* stream);
+
+/* Replaces conv_fft_batch(H, x) / the 4-D branch of conv_fft(H, x) (utils/utils_torch.py:35-50): out = ifft2(fft2(x) * H).real
+ * for a full complex spectrum otf [otf_batch][48*48] (interleaved complex64, otf_batch = 1 or batch), x / out [batch][48*48]. */
+GD_API int gd_conv_otf(const float* otf, int otf_batch, const float* x, float* out, int batch, void* stream);
+
 /* Per-stamp moment ellipticities (utils/fit_ellipse.py:370-399,467-548 + utils/utils_test.py:92-96):
  * e12 [batch][2]. */
 GD_API int gd_moments_e(const float* img, float* e12, int batch, void* stream);
@@ -129,6 +139,11 @@ GD_API int gd_tikhonet_forward(const GdXDense* x, int filter, float lam, const f
  * activations [Kt/CH][Ptot][CH], CH = 8 halves (fp16 modes) or 4 floats; weights as gd_pack_weights lays them out
  * for `precision`; out32 [N/4][Ptot][4] fp32).  ntaps = 9 (3x3, zero padding) or 1.  `geom7` receives
  * {H, W, Wp, S, base0, Ptot, M} for `batch` stamps of HxH pixels so the caller can pack/unpack. */
+/* Largest `chunk` gd_workspace_bytes / gd_workspace_init accept: the kernels decode GEMM rows into (stamp, y, x) with a
+ * multiply-shift division that is exact below 2^26 rows; larger chunks are rejected (GD_EBADSHAPE), never mis-decoded. */
+GD_API int gd_max_chunk(void);
+/* Test hook (host only): first n in [n_lo, n_hi) for which the kernels' multiply-shift n / d is wrong, or -1. */
+GD_API long long gd_debug_divmagic(unsigned d, unsigned n_lo, unsigned n_hi);
 GD_API int gd_debug_geom(int H, int batch, int* geom7);
 GD_API int gd_debug_tapgemm(int precision, int H, int batch, int ntaps, int Kt, int N, int relu, const void* act,
                             const void* weights, float* out32, void* stream);

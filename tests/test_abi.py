@@ -52,3 +52,28 @@ def test_library_is_sm100a_native():
     # tcgen05.mma, TMEM loads, bulk-async copies; cluster-multicast weight stages + multicast tcgen05.commit + cluster barrier
     for mnemonic in ('UTCHMMA', 'LDTM', 'UBLKCP', 'UBLKCP.S.G.MULTICAST', 'UTCBAR.MULTICAST', 'UCGABAR_ARV'):
         assert mnemonic in sass, mnemonic
+
+
+def test_row_decode_division_is_exact_up_to_the_largest_admitted_chunk():
+    """div_by_magic (csrc/gd_common.cuh) is exact only below 2^26 rows.  The library must (a) be exact on that
+    whole range for every divisor the geometry uses (S and Wp of the four levels), and (b) refuse chunks that would exceed it."""
+    import os
+    from gdeconv import _lib, engine
+    lib = _lib.lib
+    for H in (48, 24, 12, 6):
+        for d in ((H + 1) * (H + 1), H + 1):
+            assert lib.gd_debug_divmagic(d, 0, 1 << 26) == -1, d
+    cmax = lib.gd_max_chunk()
+    assert 27000 < cmax < 28000
+    for arch in (0, 1):
+        assert lib.gd_workspace_bytes(arch, 1, cmax) > 0
+        assert lib.gd_workspace_bytes(arch, 1, cmax + 1) == 0          # rejected, not mis-decoded
+    old = os.environ.get('GDECONV_CHUNK')
+    os.environ['GDECONV_CHUNK'] = '1000000'
+    try:
+        assert engine.max_chunk() == cmax
+    finally:
+        if old is None:
+            del os.environ['GDECONV_CHUNK']
+        else:
+            os.environ['GDECONV_CHUNK'] = old

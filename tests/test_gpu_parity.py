@@ -213,26 +213,6 @@ def test_chunking_and_ragged_batches_are_bit_identical(dev, monkeypatch):
     assert empty.shape == (0, 1, 48, 48)
 
 
-def test_layer_chained_kernel_matches(golden, dev):
-    """conv_chain.cu (GDECONV_CHAIN=1, off by default): four layers of a level software-pipelined in one launch with
-    cross-CTA flags must give the same result as one launch per layer, to accumulation-order noise (identical MMAs)."""
-    import subprocess, sys, os
-    from conftest import ROOT
-    code = (
-        "import sys, torch; sys.path[:0]=[r'%s', r'%s']\n"
-        "import oracle.ref_models as O\n"
-        "from models.unrolled_admm_gaussian import UnrolledADMMGaussian\n"
-        "g=torch.load(r'%s')\n"
-        "m=UnrolledADMMGaussian(4).eval(); m.load_state_dict(O.seeded_state_dict(lambda: O.UnrolledADMMGaussian(4), g['seeds']['G4'])); m=m.cuda()\n"
-        "i=g['inputs']; out=m(i['y'].cuda(), i['psf'].cuda(), i['alpha'].cuda()).cpu()\n"
-        "ref=g['out']['G4']; e=((out-ref).flatten(1).norm(dim=1)/ref.flatten(1).norm(dim=1)).max().item()\n"
-        "print('ERR', e)\n") % (os.path.join(ROOT, 'galaxy-deconv_b200'), ROOT, os.path.join(ROOT, 'tests', 'golden', 'golden_v1.pt'))
-    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300, env=dict(os.environ, GDECONV_CHAIN='1'))
-    assert r.returncode == 0, r.stderr[-2000:]
-    err = float(r.stdout.split('ERR')[1])
-    assert err < TOL_STAMP, err
-
-
 def test_weight_reload_is_picked_up(golden, dev, monkeypatch):
     from models.unrolled_admm_gaussian import UnrolledADMMGaussian
     monkeypatch.setenv('GDECONV_PRECISION', 'fp16_umma')

@@ -1,27 +1,40 @@
 #!/usr/bin/env python
-"""Throughput of every BASELINE.json config on one B200 (the headline config is bench.py; this covers the rest):
-  1  single galaxy latency, G(8) and U(8), on the tutorial stamp (golden fixture stamp 0 = tutorials/obs.pth + psf.pth)
+"""The BASELINE.json configs other than the headline (bench.py --config 3|4|5; config 2 is bench.py's default line), plus
+config 1 and the n = 2/4/8 / path-U lines when run directly on one GPU:
+
+  1  single-galaxy latency, G(8) and U(8), on the tutorial stamp (golden fixture stamp 0 = tutorials/obs.pth + psf.pth)
   2  Unrolled-ADMM(2/4/8) on 10,000 synthetic stamps (path G), and U(8)
-  4  Richardson-Lucy(10/50/100), Wiener, Tikhonov-Laplacian on N synthetic stamps (default 1,000,000)
-  5  PSF-mismatch sweep (shape of test_psf.py): G(8) on stamps blurred with the true PSF, deconvolved with a sheared /
-     widened model PSF; median |e - e_gt| of the moment ellipticities per point (reduced to --sweep-stamps per point)
-Prints one JSON object per line; run under gpurun and redirect into profiles/.
+  3  Unrolled-ADMM(8) on 1,000,000 stamps sharded by galaxy over the ranks (STRONG scaling), generated per shard on the device,
+     moment ellipticities + NCCL all-gather inside the timed region
+  4  Richardson-Lucy(10/50/100), Wiener, Tikhonov-Laplacian, Tikhonet_Laplacian on 1,000,000 stamps, sharded
+  5  PSF-mismatch sweep (test_psf.py:237-242 shape): 10 shear + 10 seeing errors x 100,000 stamps, sharded; median |e - e_gt|
+
+Every line is one JSON object printed by rank 0; times are CUDA events on the device, max over ranks, between barriers.
+
+    python tools/bench_configs.py                      # configs 1 and 2 on cuda:0
+    python bench.py --config 3 [--total N]             # also under torchrun with --gpus N
 """
 import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, 'galaxy-deconv_b200'), ROOT]
 
 import torch  # noqa: E402
 
+PIECE = 20000          # stamps generated per call of the (torch-on-device) generator: bounds its 4x oversampled scratch
 
-def timed(fn, steps=3, warmup=2):
+
+def _timed(fn, dev, world, steps=2, warmup=1):
+    """ms per step: CUDA events on the current stream, barrier + synchronize on both sides, max over ranks."""
+    import torch.distributed as dist
     for _ in range(warmup):
         fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -29,24 +42,110 @@ def timed(fn, steps=3, warmup=2):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms) / steps
+
+
+def _make_shard(lo, hi, dev, keys=('obs', 'psf', 'alpha'), **kw):
+    """stamps [lo, hi) generated on the device in pieces; returns dict of [n,...] tensors"""
+    from gdsynth import make_batch
+    n = hi - lo
+    shapes = dict(obs=(n, 1, 48, 48), psf=(n, 1, 48, 48), gt=(n, 1, 48, 48), alpha=(n, 1, 1, 1))
+    out = {k: torch.empty(shapes[k], device=dev) for k in keys}
+    for s in range(0, n, PIECE):
+        m = min(PIECE, n - s)
+        b = make_batch(lo + s, m, 100.0, device=dev, **kw)
+        for k in keys:
+            out[k][s:s + m] = b[k]
+    return out
+
+
+def run_config(args, model, dev, rank, world, P):
+    """bench.py --config 3|4|5.  `model` = UnrolledADMMGaussian(n_iters) on `dev` with the bench's seeded weights."""
+    from gdeconv import moments_e
+    from gdeconv.shard import gather_ellipticities, shard_range
+    from models.Richard_Lucy import Richard_Lucy
+    from models.Tikhonet import Tikhonet, Tikhonov
+    from models.Wiener import Wiener
+
+    def out(**kw):
+        if rank == 0:
+            print(json.dumps(dict(kw, n_gpus=world, data='synthetic')), flush=True)
+
+    F = args.n_iters * 1248362496 + 5742720 + 128 * args.n_iters
+    if args.config == 3:
+        N = args.total
+        lo, hi = shard_range(N, rank, world)
+        d = _make_shard(lo, hi, dev)
+
+        def step():
+            return gather_ellipticities(moments_e(model(d['obs'], d['psf'], d['alpha'])), N)
+        ms = _timed(step, dev, world, steps=max(1, args.steps), warmup=1)
+        gps = N / ms * 1e3
+        out(config=3, metric=f'galaxies/sec Unrolled-ADMM({args.n_iters}) 48x48', value=gps, unit='galaxies/s', ms_per_step=ms, scaling='strong',
+            total_stamps=N, stamps_per_gpu=hi - lo, higher_is_better=True,
+            workload=f'UnrolledADMMGaussian({args.n_iters}) on {N} synthetic stamps in total, sharded by galaxy, generated per shard on the device; '
+                     'forward + moment ellipticities + NCCL all-gather inside the timed region',
+            frac_of_sustained_tensor_peak=gps * F / 1e12 / world / P['tensor_sustained'])
+    elif args.config == 4:
+        N = args.total
+        lo, hi = shard_range(N, rank, world)
+        d = _make_shard(lo, hi, dev)
+        n = hi - lo
+        tk = Tikhonet('Laplacian').eval().to(dev)       # seeded weights: throughput only (trained-weight parity: tests/test_tikhonet.py)
+        rows = (('Wiener', lambda: Wiener()(d['obs'], d['psf'], d['alpha']), 27652),
+                ('Tikhonov_Laplacian', lambda: Tikhonov('Laplacian')(d['obs'], d['psf'], d['alpha'], 1.0), 27652),
+                ('Richard_Lucy(10)', lambda: Richard_Lucy(10)(d['obs'], d['psf']), 27648),
+                ('Richard_Lucy(50)', lambda: Richard_Lucy(50)(d['obs'], d['psf']), 27648),
+                ('Richard_Lucy(100)', lambda: Richard_Lucy(100)(d['obs'], d['psf']), 27648),
+                ('Tikhonet_Laplacian', lambda: tk(d['obs'], d['psf'], d['alpha']), 27652))
+        for name, fn, nbytes in rows:
+            ms = _timed(lambda: gather_ellipticities(moments_e(fn()), N), dev, world, steps=2, warmup=1)
+            gps = N / ms * 1e3
+            out(config=4, model=name, metric='galaxies/sec', value=gps, unit='galaxies/s', ms_per_step=ms, scaling='strong', total_stamps=N,
+                stamps_per_gpu=n, hbm_gbs_per_gpu=gps * nbytes / 1e9 / world, hbm_frac_of_measured=gps * nbytes / 1e9 / world / P['hbm'],
+                note='solver + moment ellipticities + all-gather inside the timed region')
+    else:
+        N = args.sweep_stamps
+        lo, hi = shard_range(N, rank, world)
+        errs = (0.003, 0.005, 0.01, 0.02, 0.03, 0.05, 0.07, 0.1, 0.15, 0.2)       # test_psf.py:237,242
+        base = _make_shard(lo, hi, dev, keys=('obs', 'alpha', 'gt'))
+        e_gt = gather_ellipticities(moments_e(base['gt']), N)
+        t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t_all0.record()
+        for kind in ('shear', 'fwhm'):
+            for err in errs:
+                kw = dict(psf_shear_err=err) if kind == 'shear' else dict(psf_fwhm_err=err)
+                psf = _make_shard(lo, hi, dev, keys=('psf',), **kw)['psf']        # the mismatched model PSF (obs is unchanged)
+                box = {}
+
+                def step():
+                    box['e'] = gather_ellipticities(moments_e(model(base['obs'], psf, base['alpha'])), N)
+                ms = _timed(step, dev, world, steps=1, warmup=0)
+                de = (box['e'] - e_gt).norm(dim=1)
+                out(config=5, sweep=kind, err=err, total_stamps=N, stamps_per_gpu=hi - lo, ms_per_point=ms, value=N / ms * 1e3, unit='galaxies/s',
+                    median_abs_de=float(de.median()),
+                    note='seeded RANDOM weights (trained weights absent from the checkout): throughput shape only, not an accuracy claim')
+        t_all1.record()
+        torch.cuda.synchronize()
+        out(config=5, sweep='all', points=2 * len(errs), total_stamps=N, seconds_including_psf_generation=t_all0.elapsed_time(t_all1) / 1e3)
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--solver-stamps', type=int, default=1000000)
-    ap.add_argument('--sweep-stamps', type=int, default=10000)
-    args = ap.parse_args()
+    ap.parse_args()
     import oracle.ref_models as O               # seeded weights only
-    from gdeconv import moments_e
-    from gdeconv.synth import make_batch
+    from gdsynth import make_batch
     from models.unrolled_admm_gaussian import UnrolledADMMGaussian
     from models.Unrolled_ADMM import Unrolled_ADMM
-    from models.Richard_Lucy import Richard_Lucy
-    from models.Wiener import Wiener
-    from models.Tikhonet import Tikhonov, Tikhonet
     dev = torch.device('cuda:0')
     out = lambda **kw: print(json.dumps(kw), flush=True)
+    timed = lambda fn, steps=3, warmup=2: _timed(fn, dev, 1, steps, warmup)
 
     # ---- config 1: single galaxy --------------------------------------------------------------------------------
     g = torch.load(os.path.join(ROOT, 'tests', 'golden', 'golden_v1.pt'))
@@ -59,7 +158,7 @@ def main():
     mu = mu.to(dev)
     for name, m in (('UnrolledADMMGaussian(8)', mg), ('Unrolled_ADMM(8,Gaussian)', mu)):
         ms = timed(lambda: m(y1, k1, a1), steps=20, warmup=5)
-        out(config=1, model=name, batch=1, ms_per_galaxy=ms, note='tutorial stamp, device-resident input, includes ~400 kernel launches')
+        out(config=1, model=name, batch=1, ms_per_galaxy=ms, note='tutorial stamp, device-resident input')
 
     # ---- config 2: 10k stamps, n = 2/4/8 ---------------------------------------------------------------------------
     b = make_batch(0, 10000, 100.0, device=dev)
@@ -70,43 +169,6 @@ def main():
     ms = timed(lambda: mu(b['obs'], b['psf'], b['alpha']), steps=2, warmup=1)
     out(config=2, model='Unrolled_ADMM(8,Gaussian) nc 64..512', stamps=10000, ms_per_step=ms, galaxies_per_s=10000 / ms * 1e3,
         flops_per_stamp=39910877312, tflops=10000 / ms * 1e3 * 39910877312 / 1e12)
-
-    # ---- config 5 (reduced): PSF mismatch sweep -------------------------------------------------------------------
-    ns = args.sweep_stamps
-    gt_e = None
-    for kind, errs in (('shear', (0.0, 0.01, 0.05, 0.1, 0.2)), ('fwhm', (0.01, 0.05, 0.1, 0.2))):
-        for err in errs:
-            bb = make_batch(0, ns, 100.0, device=dev, psf_shear_err=err if kind == 'shear' else 0.0, psf_fwhm_err=err if kind == 'fwhm' else 0.0)
-            if gt_e is None:
-                gt_e = moments_e(bb['gt'])
-            t0 = time.perf_counter()
-            e = moments_e(mg(bb['obs'], bb['psf'], bb['alpha']))
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            de = (e - gt_e).norm(dim=1)
-            out(config=5, sweep=kind, err=err, stamps=ns, median_abs_de=float(de.median()), seconds=dt,
-                note='seeded RANDOM weights (trained weights absent from the checkout): throughput shape only, not an accuracy claim')
-    del bb
-
-    # ---- config 4: classical solvers on N stamps ---------------------------------------------------------------------
-    N = args.solver_stamps
-    piece = 20000
-    obs = torch.empty(N, 1, 48, 48, device=dev); psf = torch.empty_like(obs); alpha = torch.empty(N, 1, 1, 1, device=dev)
-    for s in range(0, N, piece):
-        bb = make_batch(s, min(piece, N - s), 100.0, device=dev)
-        obs[s:s + piece], psf[s:s + piece], alpha[s:s + piece] = bb['obs'], bb['psf'], bb['alpha']
-    del bb
-    hbm = 6554.6
-    tk = Tikhonet('Laplacian').eval().to(dev)                # seeded weights: throughput only (trained-weight parity: tests/test_tikhonet.py)
-    nt = min(N, 100000)
-    ms = timed(lambda: tk(obs[:nt], psf[:nt], alpha[:nt]), steps=2, warmup=1)
-    out(config=4, model='Tikhonet_Laplacian (Tikhonov + XDenseUNet, fp32 CUDA cores)', stamps=nt, ms_per_step=ms, galaxies_per_s=nt / ms * 1e3)
-    for name, fn, nbytes in (('Wiener', lambda: Wiener()(obs, psf, alpha), 27652), ('Tikhonov_Laplacian', lambda: Tikhonov('Laplacian')(obs, psf, alpha, 1.0), 27652),
-                             ('Richard_Lucy(10)', lambda: Richard_Lucy(10)(obs, psf), 27648), ('Richard_Lucy(50)', lambda: Richard_Lucy(50)(obs, psf), 27648),
-                             ('Richard_Lucy(100)', lambda: Richard_Lucy(100)(obs, psf), 27648)):
-        ms = timed(fn, steps=2, warmup=1)
-        gps = N / ms * 1e3
-        out(config=4, model=name, stamps=N, ms_per_step=ms, galaxies_per_s=gps, hbm_gbs=gps * nbytes / 1e9, hbm_frac_of_measured=gps * nbytes / 1e9 / hbm)
 
 
 if __name__ == '__main__':
