@@ -583,8 +583,10 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
     auto down_stage = [&](int L, int s0, int n) -> int {          // m_down{L+1} (ResUNet.py:32-34)
         if (L == 0 && l1chain) {
             const void* w4[4] = {W->down_rb[0][0][0], W->down_rb[0][0][1], W->down_rb[0][1][0], W->down_rb[0][1][1]};
-            GD_TRY(launch_l1chain_down(g[0], g[1], n, t + (size_t)s0 * NPIX, W->head_h, w4, at(ws.d16[1], 1, s0), st));
-        } else
+            // ... and the k2s2 strided conv of m_down1 (its space-to-depth operand never leaves shared memory)
+            return launch_l1chain_down(g[0], g[1], n, t + (size_t)s0 * NPIX, W->head_h, w4, W->down[0], (float*)at(ws.skip32[1], 1, s0),
+                                       at(ws.a16[1], 1, s0), st);
+        }
         GD_TRY(resblock_pair(L, s0, n, W->down_rb[L][0], W->down_rb[L][1], ws.skip32[L], ws.p32a[L], ws.a16[L], ws.p32a[L], nullptr,
                              nullptr, nullptr, ws.d16[L + 1]));
         ConvParams p = conv_base(g[L + 1], n);         // k2s2 strided conv as a 1-tap GEMM on the space-to-depth copy

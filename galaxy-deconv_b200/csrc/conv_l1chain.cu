@@ -20,6 +20,12 @@
 // is issued as soon as the epilogues of the layer-l tiles under its 3x3 footprint have arrived (per-tile mbarriers), so the
 // tensor pipe never drains at a layer boundary.
 //
+// Tried and rejected in round 2 (profiles/README_r02.md): concatenating the three dx taps of a kernel row along N (three N = 96 MMAs
+// per K16 step on one A window instead of nine N = 32 ones, the epilogue adding the neighbouring lanes' partial sums by warp
+// shuffles + a shared-memory exchange at warp boundaries).  Bit-for-bit the same results and a third of the A-operand fetches,
+// but the epilogue grew to ~575 instructions per tile and warp (64 shuffles, 64 adds, hi/lo conversions of the then packed
+// stream) and became the bound: 2.3 ms per launch instead of 1.5 ms.
+//
 // Warp roles (512 threads, one persistent CTA per SM):
 //   warp 0      producer: weight slots; UP: the item's hi -> X and lo -> T windows; DOWN: 29 rows of t (bulk async copies)
 //   warps 1-3   MMA issuers, warp 1 + j owns tile j of every 3-tile unit (one elected lane each, straight-line 18 MMAs); warp 1 allocates TMEM
@@ -55,10 +61,16 @@ constexpr int LC_STREAM_TILES = 10;
 constexpr int LC_J = 3;                              // tiles per MMA unit = MMA-issuing warps
 constexpr int LC_ACC_COL = LC_STREAM_TILES * LC_C;   // 320: two accumulator stages of LC_J x 32 columns follow the stream (512 in all)
 constexpr int LC_HEAD_TILES = 11;
+// DOWN: the m_down1 strided conv (k2 s2, 32 -> 64 channels; models/resnet_basicblock.py:73-79) runs in the same kernel: the epilogue of
+// the 4th conv writes the item's own 24 rows as a space-to-depth operand [16 chunks][304 coarse rows][8] over the (then idle) X
+// planes, three M128 N64 K128 GEMM tiles follow, and their epilogue stores x2 = the level-1 skip (fp32) + its fp16 operand copy.
+constexpr int LC_SR = 304;                           // rows per chunk plane of the space-to-depth operand (12 coarse rows x 25 = 300 used)
+constexpr int LC_WD_BYTES = 4 * LC_C * 2 * LC_C * 2; // 16,384: packed strided-conv weights [16][64][8]
+constexpr int LC_DN = 2 * LC_C;                      // 64 output channels
 
 enum { LCB_W_FULL = 0, LCB_W_EMPTY = 2, LCB_ACC_FULL = 4, LCB_ACC_EMPTY = 6, LCB_X_FULL = 8, LCB_T_FULL = 9, LCB_X_FREE = 10,
-       LCB_T_FREE = 11, LCB_ITEM_DONE = 12, LCB_X_READY = 13, LCB_TILE_DONE = LCB_X_READY + LC_HEAD_TILES, LCB_S_READY = LCB_TILE_DONE + 3 * 11,
-       LCB_TWIN_FULL = LCB_S_READY + LC_STREAM_TILES, LCB_TWIN_EMPTY, LCB_COUNT };
+       LCB_T_FREE = 11, LCB_ITEM_DONE = 12, LCB_X_READY = 13, LCB_TILE_DONE = LCB_X_READY + LC_HEAD_TILES, LCB_S_READY = LCB_TILE_DONE + 4 * 11,
+       LCB_TWIN_FULL = LCB_S_READY + LC_STREAM_TILES, LCB_TWIN_EMPTY, LCB_DOWN_FULL, LCB_DOWN_EMPTY, LCB_COUNT };
 
 struct L1ChainParams {
     int nb;                        // stamps
@@ -66,7 +78,9 @@ struct L1ChainParams {
     const float* t;                // DOWN: scaled denoiser input [nb][48*48]
     const void *x_hi, *x_lo;       // UP: fp16 hi/lo planes of the m_up1 transposed-conv output [4][g0.Ptot][8]
     const void* w[4];              // packed 3x3 weights [tap][4][32][8]: block 1 conv 1, conv 2, block 2 conv 1, conv 2
-    void* s2d;                     // DOWN: space-to-depth copy [16][g1.Ptot][8] for the strided conv
+    const void* wdown;             // DOWN: packed strided-conv weights [16][64][8] (K = (dy*2+dx)*32 + ci)
+    float* skip32;                 // DOWN: x2 fp32 [16][g1.Ptot][4] (U-Net skip + residual of the next level)
+    void* x2_16;                   // DOWN: x2 fp16 [8][g1.Ptot][8] (operand of the next conv)
     float* tail_part;              // UP: [9][g0.Ptot] per-tap m_tail partial sums
 };
 struct L1ChainHT { float head[9 * LC_C], tail[9 * LC_C]; };
@@ -118,7 +132,8 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
         mbar_init(bar(LCB_X_FULL), 1); mbar_init(bar(LCB_T_FULL), 1); mbar_init(bar(LCB_X_FREE), LC_J); mbar_init(bar(LCB_T_FREE), LC_J);
         mbar_init(bar(LCB_ITEM_DONE), 8);
         for (int j = 0; j < LC_HEAD_TILES; ++j) mbar_init(bar(LCB_X_READY + j), 4);
-        for (int j = 0; j < 33; ++j) mbar_init(bar(LCB_TILE_DONE + j), 4);
+        for (int j = 0; j < 44; ++j) mbar_init(bar(LCB_TILE_DONE + j), 4);
+        mbar_init(bar(LCB_DOWN_FULL), LC_J); mbar_init(bar(LCB_DOWN_EMPTY), 8);
         for (int j = 0; j < LC_STREAM_TILES; ++j) mbar_init(bar(LCB_S_READY + j), 4);
         mbar_init(bar(LCB_TWIN_FULL), 1); mbar_init(bar(LCB_TWIN_EMPTY), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -139,20 +154,64 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
     const int total_items = 2 * p.nb;
     const int n_my = total_items > (int)blockIdx.x ? (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const uint32_t Ptot0 = (uint32_t)p.g0.Ptot;
+    constexpr int NLAYERS = MODE == 0 ? 5 : 4;
     // byte offset of row s of plane pl inside the activation region
     auto row_off = [](int pl, int s) { return (uint32_t)((pl * LC_PSTRIDE + LC_GAP + s) * 16); };
+
+    // DOWN: x1 = m_head(t) of local row s of a top (h = 0) / bottom (h = 1) item from the t window in shared memory (zeros outside the
+    // window / on pad pixels); weights are constant-bank operands
+    auto head_row = [&](int h, int s, float* acc) -> bool {
+        const int ylo = h ? LC_BOT_Y0 - 1 : 0;                   // first image row held by the t window
+        const int yq = s >= 0 ? (s * 1338) >> 16 : 0, x = s - yq * LC_WP;
+        const bool inimg = s >= 0 && s < LC_ROWS && x < STAMP;
+        const int y = h * LC_BOT_Y0 + yq;
+        float in[9];
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int yy = y + dy, xx = x + dx;
+                in[(dy + 1) * 3 + dx + 1] = (inimg && yy >= 0 && yy < STAMP && xx >= 0 && xx < STAMP) ? twin[(yy - ylo) * STAMP + xx] : 0.f;
+            }
+#pragma unroll
+        for (int c = 0; c < LC_C; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+            for (int c = 0; c < LC_C; ++c) acc[c] = fmaf(in[tp], htw.head[tp * LC_C + c], acc[c]);
+        return inimg;
+    };
+    // DOWN, X fill: head tile j (128 rows) by the four warps of one set (q = TMEM-independent quarter index).  The space-to-depth
+    // operand of the previous item overwrote pad pixels and inter-plane gaps of X, so from the second item on every row is rewritten
+    // (zeros where there is no pixel).  The fill (~900 cycles per tile on the four helper warps) can no longer overlap the previous
+    // item's last conv, because the strided conv's operand occupies X until then: measured, the in-kernel strided conv costs 0.33 ms
+    // per launch and replaces a 0.45 ms launch + 1.5 GB of HBM traffic (sharing the fill with the epilogue warps was slower still).
+    auto fill_x_tile = [&](int h, int k, int j, int q) {
+        const int s = lc_head_start(h, j) + q * 32 + lane;
+        float acc[LC_C];
+        const bool inimg = head_row(h, s, acc);
+        if (inimg || (k > 0 && s >= 0 && s < LC_PSTRIDE)) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(smem + row_off(ch, s)) = pack8_half(acc + 8 * ch);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(LCB_X_READY + j));
+    };
 
     if (warp == 0) {
         // ===== producer =====
         if (lane == 0) {
+            // weight layers of an item: the four 3x3 convs (+ the strided conv, DOWN); layer counter Lc picks the slot
             auto load_w = [&](int k, int L) {
-                const int Lc = 4 * k + L, slot = Lc & 1;
+                const int Lc = NLAYERS * k + L, slot = Lc & 1;
+                const uint32_t bytes = L < 4 ? (uint32_t)LC_W_BYTES : (uint32_t)LC_WD_BYTES;
                 mbar_wait(bar(LCB_W_EMPTY + slot), ((Lc >> 1) & 1) ^ 1);
-                mbar_expect_tx(bar(LCB_W_FULL + slot), (uint32_t)LC_W_BYTES);
+                mbar_expect_tx(bar(LCB_W_FULL + slot), bytes);
                 const uint32_t dst = smem_u32(w_smem) + (uint32_t)slot * LC_W_BYTES;
-                const unsigned char* src = reinterpret_cast<const unsigned char*>(p.w[L]);
-                bulk_g2s(dst, src, LC_W_BYTES / 2, bar(LCB_W_FULL + slot));
-                bulk_g2s(dst + LC_W_BYTES / 2, src + LC_W_BYTES / 2, LC_W_BYTES / 2, bar(LCB_W_FULL + slot));
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(L < 4 ? p.w[L] : p.wdown);
+                bulk_g2s(dst, src, bytes / 2, bar(LCB_W_FULL + slot));
+                bulk_g2s(dst + bytes / 2, src + bytes / 2, bytes / 2, bar(LCB_W_FULL + slot));
             };
             auto load_act = [&](int it, const void* src, int pl0, uint32_t full) {
                 const int b = it >> 1, h = it & 1;
@@ -175,6 +234,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
                 load_w(k, 0);
                 if (MODE == 1) { mbar_wait(bar(LCB_T_FREE), (k & 1) ^ 1); load_act(it, p.x_lo, 4, bar(LCB_T_FULL)); }
                 load_w(k, 1); load_w(k, 2); load_w(k, 3);
+                if (MODE == 0) load_w(k, 4);
             }
         }
     } else if (warp <= LC_J) {
@@ -190,8 +250,9 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
         for (int k = 0; k < n_my; ++k) {
             const int it = (int)blockIdx.x + k * (int)gridDim.x, h = it & 1;
             const uint32_t kp = (uint32_t)(k & 1);
+            if (MODE == 0) mbar_wait(bar(LCB_DOWN_EMPTY), kp ^ 1);       // the previous item's strided-conv accumulators have been read
             for (int L = 0; L < 4; ++L) {
-                const int Lc = 4 * k + L, slot = Lc & 1;
+                const int Lc = NLAYERS * k + L, slot = Lc & 1;
                 mbar_wait(bar(LCB_W_FULL + slot), (Lc >> 1) & 1);
                 const int n = lc_ntiles(L), nprev = L == 0 ? LC_HEAD_TILES : lc_ntiles(L - 1);
                 const int src_pl = (L & 1) ? 4 : 0;       // conv 1 of a block reads X, conv 2 reads T
@@ -237,6 +298,27 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
                 }
                 __syncwarp();
             }
+            if (MODE == 0) {
+                // ---- strided conv: tile jw = coarse rows [128 jw, +128) of the item, D = 64 columns at LC_ACC_COL + 64 jw ----
+                const int Lc = NLAYERS * k + 4, slot = Lc & 1;
+                mbar_wait(bar(LCB_W_FULL + slot), (Lc >> 1) & 1);
+                for (int i = 0; i < lc_ntiles(3); ++i) mbar_wait(bar(LCB_TILE_DONE + 3 * 11 + i), kp);   // operand complete, accumulators drained
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t dd = tmem + (uint32_t)(LC_ACC_COL + jw * LC_DN);
+                    const uint64_t ad = smem_desc(smem_u32(smem) + row_off(0, 0), LC_SR * 16, 128) + (uint64_t)(uint32_t)(jw * MTILE);
+                    const uint64_t bd = smem_desc(smem_u32(w_smem) + (uint32_t)slot * LC_W_BYTES, LC_DN * 16, 128);
+                    const uint32_t idd = instr_desc_f16(MTILE, LC_DN);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        if (ks == 0) tc_mma_f16(dd, ad, bd, idd, 0u);
+                        else tc_mma_f16_acc(dd, ad + (uint64_t)(ks * 2 * LC_SR), bd + (uint64_t)(ks * 2 * LC_DN), idd);
+                    }
+                    tc_commit(bar(LCB_DOWN_FULL));
+                    tc_commit(bar(LCB_W_EMPTY + slot));
+                }
+                __syncwarp();
+            }
         }
     } else if (warp < LC_J + 5) {
         // ===== helpers =====
@@ -249,47 +331,22 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
             const int it = (int)blockIdx.x + k * (int)gridDim.x, h = it & 1;
             const uint32_t kp = (uint32_t)(k & 1);
             if (MODE == 0) {
-                const int ylo = h ? LC_BOT_Y0 - 1 : 0;                   // first image row held by the t window
-                // x1 of local row s (zeros outside the window / on pad pixels)
-                auto head_row = [&](int s, float* acc) -> bool {
-                    const int yq = s >= 0 ? (s * 1338) >> 16 : 0, x = s - yq * LC_WP;
-                    const bool inimg = s >= 0 && s < LC_ROWS && x < STAMP;
-                    const int y = h * LC_BOT_Y0 + yq;
-                    float in[9];
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            const int yy = y + dy, xx = x + dx;
-                            in[(dy + 1) * 3 + dx + 1] = (inimg && yy >= 0 && yy < STAMP && xx >= 0 && xx < STAMP) ? twin[(yy - ylo) * STAMP + xx] : 0.f;
-                        }
-#pragma unroll
-                    for (int c = 0; c < LC_C; ++c) acc[c] = 0.f;
-#pragma unroll
-                    for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-                        for (int c = 0; c < LC_C; ++c) acc[c] = fmaf(in[tp], htw.head[tp * LC_C + c], acc[c]);
-                    return inimg;
-                };
-                mbar_wait(bar(LCB_X_FREE), kp ^ 1);                      // the previous item's last reads of X have completed
+                mbar_wait(bar(LCB_DOWN_FULL), kp ^ 1);                   // the previous item's strided conv has finished reading the X planes
                 mbar_wait(bar(LCB_TWIN_FULL), kp);
-                for (int j = 0; j < LC_HEAD_TILES; ++j) {
-                    const int s = lc_head_start(h, j) + q * 32 + lane;
-                    float acc[LC_C];
-                    if (head_row(s, acc)) {
+                if (k > 0) {                                             // gap rows below the window, which no head tile covers
+                    const int s = LC_ROWS + q * 32 + lane;
+                    if (s < LC_PSTRIDE) {
 #pragma unroll
-                        for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(smem + row_off(ch, s)) = pack8_half(acc + 8 * ch);
+                        for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(smem + row_off(ch, s)) = make_uint4(0u, 0u, 0u, 0u);
                     }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(LCB_X_READY + j));
                 }
+                for (int j = 0; j < LC_HEAD_TILES; ++j) fill_x_tile(h, k, j, q);
                 mbar_wait(bar(LCB_ITEM_DONE), kp ^ 1);                   // the previous item's stream has been consumed
                 tc_fence_after();
                 for (int i = 0; i < LC_STREAM_TILES; ++i) {
                     const int s = lc_stream_start(h, i) + q * 32 + lane;
                     float acc[LC_C];
-                    head_row(s, acc);
+                    head_row(h, s, acc);
                     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * LC_C);
                     uint32_t u[LC_C];
 #pragma unroll
@@ -405,23 +462,60 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive(bar(LCB_TILE_DONE + L * 11 + i));
                             } else {
-                                // second conv of block 2: the item's own 24 rows leave the SM
+                                // second conv of block 2: the item's own 24 rows leave the SM (UP) / become the strided conv's operand (DOWN)
                                 const bool own = wr && (h ? s >= LC_ROWS - LC_OWN : s < LC_OWN);
+                                if (MODE == 0) mbar_wait(bar(LCB_X_FREE), kp);      // conv 3 has finished reading the X planes the operand overwrites
                                 if (own) {
                                     const int y = h * LC_BOT_Y0 + yq;
                                     if (MODE == 0) {
-                                        const Geom& g1 = p.g1;
-                                        const int crow = g1.base0 + bst * g1.S + (y >> 1) * g1.Wp + (x >> 1), ctap = ((y & 1) << 1) | (x & 1);
-                                        uint4* dst = reinterpret_cast<uint4*>(p.s2d) + (size_t)(ctap * 4) * g1.Ptot + crow;
+                                        // space-to-depth operand of the strided conv: K chunk = (dy*2+dx)*4 + ch, row = coarse pixel of the item
+                                        const int yl = yq - (h ? LC_WIN_Y - 24 : 0);
+                                        const int cr = (yl >> 1) * 25 + (x >> 1), ctap = ((yl & 1) << 1) | (x & 1);
+                                        unsigned char* dst = smem + row_off(0, 0) + (uint32_t)((ctap * 4 * LC_SR + cr) * 16);
 #pragma unroll
-                                        for (int ch = 0; ch < 4; ++ch) dst[(size_t)ch * g1.Ptot] = pack8_half(v + 8 * ch);
+                                        for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(dst + ch * LC_SR * 16) = pack8_half(v + 8 * ch);
                                     } else {
                                         float* dst = p.tail_part + ((size_t)p.g0.base0 + (size_t)bst * p.g0.S + (size_t)(y * LC_WP + x));
                                         lc_tail(htw.tail, v, dst, Ptot0);
                                     }
                                 }
+                                if (MODE == 0) {
+                                    fence_proxy_async_smem();
+                                    __syncwarp();
+                                    if (lane == 0) mbar_arrive(bar(LCB_TILE_DONE + L * 11 + i));
+                                }
                             }
                         }
+                    }
+                }
+            }
+            if (MODE == 0) {
+                // ---- strided-conv epilogue: warp (q, grp) stores channels [32 grp, +32) of coarse rows 128 j + 32 q + lane, j = 0..2 ----
+                mbar_wait(bar(LCB_DOWN_FULL), kp);
+                tc_fence_after();
+                const Geom& g1 = p.g1;
+                for (int j = 0; j < 3; ++j) {
+                    const uint32_t a = tmem + lane_base + (uint32_t)(LC_ACC_COL + j * LC_DN + grp * 32);
+                    uint32_t d0[16], d1[16];
+                    tc_ld16_nowait(a, d0); tc_ld16_nowait(a + 16, d1);
+                    const int cr = j * MTILE + q * 32 + lane, cx = cr % 25;
+                    tc_ld_wait16(d0); tc_ld_wait16(d1);
+                    if (j == 2) {                    // every accumulator column of the strided conv has been read
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(LCB_DOWN_EMPTY));
+                    }
+                    if (cr < 300 && cx < 24) {
+                        const size_t row = (size_t)g1.base0 + (size_t)bst * g1.S + (size_t)(h * 300 + cr);
+                        float4* o32 = reinterpret_cast<float4*>(p.skip32) + (size_t)(grp * 8) * g1.Ptot + row;
+                        uint4* o16 = reinterpret_cast<uint4*>(p.x2_16) + (size_t)(grp * 4) * g1.Ptot + row;
+                        float v[32];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) { v[c] = __uint_as_float(d0[c]); v[16 + c] = __uint_as_float(d1[c]); }
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) o32[(size_t)c4 * g1.Ptot] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8) o16[(size_t)c8 * g1.Ptot] = pack8_half(v + 8 * c8);
                     }
                 }
             }
@@ -459,7 +553,8 @@ static int l1chain_launch(int mode, const L1ChainParams& p, const float* head_w,
     if (tail_w) memcpy(hw.tail, tail_w, sizeof(hw.tail));
     const int items = 2 * p.nb, grid = items < g_lc_sms ? items : g_lc_sms;
     cudaEvent_t e1 = nullptr;
-    const double flops = 4.0 * 2.0 * (double)p.nb * NPIX * (double)LC_C * LC_C * 9;      // four 3x3 convs, valid pixels
+    double flops = 4.0 * 2.0 * (double)p.nb * NPIX * (double)LC_C * LC_C * 9;            // four 3x3 convs, valid pixels
+    if (mode == 0) flops += 2.0 * (double)p.nb * (NPIX / 4) * (4.0 * LC_C) * LC_DN;      // + the k2s2 strided conv
     { int rc = conv_profile_mark(flops, st, &e1); if (rc != GD_OK) return rc; }
     if (mode == 0) k_l1_chain<0><<<grid, LC_THREADS, LC_SMEM, st>>>(p, hw);
     else k_l1_chain<1><<<grid, LC_THREADS, LC_SMEM, st>>>(p, hw);
@@ -468,13 +563,13 @@ static int l1chain_launch(int mode, const L1ChainParams& p, const float* head_w,
     return GD_OK;
 }
 
-int launch_l1chain_down(const Geom& g0, const Geom& g1, int nb, const float* t, const float* head_w_host, const void* const* w4, void* s2d,
-                        cudaStream_t st) {
+int launch_l1chain_down(const Geom& g0, const Geom& g1, int nb, const float* t, const float* head_w_host, const void* const* w4, const void* wdown,
+                        float* skip32, void* x2_16, cudaStream_t st) {
     L1ChainParams p;
     memset(&p, 0, sizeof(p));
-    p.nb = nb; p.g0 = g0; p.g1 = g1; p.t = t; p.s2d = s2d;
+    p.nb = nb; p.g0 = g0; p.g1 = g1; p.t = t; p.wdown = wdown; p.skip32 = skip32; p.x2_16 = x2_16;
     for (int i = 0; i < 4; ++i) p.w[i] = w4[i];
-    if (!t || !head_w_host || !s2d) { set_error("conv_l1chain: down needs t, the head weights and the s2d target"); return GD_EBADSHAPE; }
+    if (!t || !head_w_host || !wdown || !skip32 || !x2_16) { set_error("conv_l1chain: down needs t, the head / strided-conv weights and the x2 outputs"); return GD_EBADSHAPE; }
     return l1chain_launch(0, p, head_w_host, nullptr, st);
 }
 

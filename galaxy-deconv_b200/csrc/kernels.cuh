@@ -14,8 +14,8 @@ int conv_profile_end(double* ms_total, double* flops_total, unsigned long long* 
 int conv_profile_mark(double flops, cudaStream_t st, cudaEvent_t* stop);
 int conv_rb_init();
 int conv_l1chain_init();
-int launch_l1chain_down(const Geom& g0, const Geom& g1, int nb, const float* t, const float* head_w_host, const void* const* w4, void* s2d,
-                        cudaStream_t st);
+int launch_l1chain_down(const Geom& g0, const Geom& g1, int nb, const float* t, const float* head_w_host, const void* const* w4, const void* wdown,
+                        float* skip32, void* x2_16, cudaStream_t st);
 int launch_l1chain_up(const Geom& g0, const Geom& g1, int nb, const void* x_hi, const void* x_lo, const float* tail_w_host, const void* const* w4,
                       float* tail_part, cudaStream_t st);
 bool conv_rb_supported(const ConvParams& p1, const ConvParams& p2);
