@@ -61,6 +61,7 @@ struct GdWeights {
     const void* body_rb[2][2];
     const void* up[3];                // k2s2 transposed conv C_{L+1} -> C_L (index = fine level L)
     const void* up_rb[3][2][2];
+    const void* up0_plain;            // C0 = 32, tcgen05 path: m_up1's transposed conv with plain column order n = (dy*2+dx)*C0 + co (conv_l1chain.cu)
     gd::SubnetParams sub;
     const float* rho_param;           // [n_rho] when subnet=False
 };
@@ -156,6 +157,17 @@ static int pack_up(Blob& bl, const GdTensorDesc* t, int Ci, int Co, int prec, si
     return GD_OK;
 }
 
+// the same transposed conv for the level-0 chain kernel: plain column order n = (dy*2+dx)*Co + co
+static int pack_up_plain(Blob& bl, const GdTensorDesc* t, int Ci, int Co, size_t* off, const char* what) {
+    if (!shape_is(t, Ci, Co, 2, 2)) GD_FAIL(GD_EBADSHAPE, "weight %s: missing or not (%d,%d,2,2)", what, Ci, Co);
+    std::vector<float> B((size_t)Ci * 4 * Co);
+    for (int ci = 0; ci < Ci; ++ci)
+        for (int co = 0; co < Co; ++co)
+            for (int tp = 0; tp < 4; ++tp) B[(size_t)ci * 4 * Co + tp * Co + co] = t->data[((size_t)ci * Co + co) * 4 + tp];
+    *off = pack_tapgemm(bl, 1, Ci, 4 * Co, PREC_FP16_UMMA, B);
+    return GD_OK;
+}
+
 static size_t pack_f32(Blob& bl, const float* src, size_t n) {
     size_t off = bl.reserve(n * sizeof(float));
     memcpy(bl.host.data() + off, src, n * sizeof(float));
@@ -247,6 +259,7 @@ extern "C" int gd_pack_weights(int arch, int n_iters, const GdTensorDesc* tensor
             snprintf(key, sizeof key, "m_up%d.0.weight", L + 1);
             GD_TRY(pack_up(bl, F.net(key), 2 * C, C, precision, &off, key));
             slot(&W.up[L], off);
+            if (L == 0 && C == 32 && precision == PREC_FP16_UMMA) { GD_TRY(pack_up_plain(bl, F.net(key), 2 * C, C, &off, key)); slot(&W.up0_plain, off); }
         }
         for (int blk = 0; blk < 2; ++blk)
             for (int j = 0; j < 2; ++j) {
@@ -352,6 +365,7 @@ struct Ws {
     // ResUNet activations
     float *skip32[4], *p32a[4], *p32b[4];
     void *a16[4], *t16[4], *d16[4], *lo16[4];   // lo16: fp16 correction planes of the hi/lo residual stream (hi = a16 / t16)
+    void* lc_scratch;                          // conv_l1chain.cu UP: per-CTA lo halves of the transposed conv's output
     float *tpad, *tail_part;                   // head/tail fusion (conv_umma.cu EPI_HT): padded-linear input, per-tap tail sums
 };
 
@@ -386,6 +400,7 @@ static Ws ws_layout(unsigned char* base, int arch, int prec, int chunk) {
         w.lo16[L] = take(n * es);
         if (L > 0) w.d16[L] = take((size_t)2 * n * es);        // 4*C_{L-1} = 2*C_L channels
     }
+    w.lc_scratch = C0 == 32 ? take(l1chain_scratch_bytes()) : nullptr;
     w.tpad = (float*)take((size_t)w.g[0].Ptot * 4);
     w.tail_part = (float*)take((size_t)(C0 / 16) * 9 * w.g[0].Ptot * 4);   // 32-channel units (conv_umma.cu) or 16-channel halves (conv_rb.cu)
     w.total = off;
@@ -595,16 +610,16 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         return run_conv(p, prec, st);
     };
     auto up_stage = [&](int L, int s0, int n) -> int {            // m_up{L+1} (ResUNet.py:36-38)
+        if (L == 0 && l1chain) {          // transposed conv + both ResBlocks + m_tail partial sums in one launch
+            const void* w4[4] = {W->up_rb[0][0][0], W->up_rb[0][0][1], W->up_rb[0][1][0], W->up_rb[0][1][1]};
+            return launch_l1chain_up(g[0], g[1], n, at(ws.a16[1], 1, s0), W->up0_plain, W->tail_h, w4, at4(ws.tail_part, s0), ws.lc_scratch, st);
+        }
         ConvParams p = conv_base(g[L + 1], n);         // k2s2 transposed conv: GEMM on the coarse level, scatter to fine
         p.ntaps = 1; p.off[0] = 0; p.Kt = C[L + 1]; p.N = 4 * C[L]; p.a = at(ws.a16[L + 1], L + 1, s0); p.w = W->up[L];
         p.mode = 1; p.Cf = C[L]; p.Cf_log2 = 0; while ((1 << p.Cf_log2) < p.Cf) ++p.Cf_log2; p.gf = g[L]; p.gf.M = n * g[L].S;
         p.out32 = (float*)at(ws.p32a[L], L, s0); p.out16 = at(ws.a16[L], L, s0);
         if (hilo) { p.out_lo = at(ws.lo16[L], L, s0); p.out32 = nullptr; }
         GD_TRY(run_conv(p, prec, st));
-        if (L == 0 && l1chain) {
-            const void* w4[4] = {W->up_rb[0][0][0], W->up_rb[0][0][1], W->up_rb[0][1][0], W->up_rb[0][1][1]};
-            return launch_l1chain_up(g[0], g[1], n, at(ws.a16[0], 0, s0), at(ws.lo16[0], 0, s0), W->tail_h, w4, at4(ws.tail_part, s0), st);
-        }
         if (L > 0) return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L],
                                         ws.skip32[L], nullptr, ws.a16[L], nullptr);
         return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L], ws.skip32[L],
@@ -737,7 +752,7 @@ extern "C" int gd_admm_forward(const GdWeights* W, int llh, int u_v0_over_alpha,
             }
         } else {
             float* u1 = ws.u;
-            GD_TRY(launch_u_prologue(yc, kc, ac, u_v0_over_alpha, ws.spec, ws.x, ws.z, ws.v, u1, ws.u2, ws.Hx, nb, st));
+            GD_TRY(launch_u_prologue(yc, kc, ac, u_v0_over_alpha & 1, ws.spec, ws.x, ws.z, ws.v, u1, ws.u2, ws.Hx, nb, st));
             auto dump = [&](int slot) -> int {
                 if (!analysis) return GD_OK;
                 float* A = analysis + (size_t)slot * 5 * plane + o;
@@ -752,7 +767,7 @@ extern "C" int gd_admm_forward(const GdWeights* W, int llh, int u_v0_over_alpha,
                 GD_TRY(launch_u_post(ws.spec, ws.rho, nr, n, it, ws.z, ws.v, ws.x, u1, ws.u2, ws.Hx, nb, st));
                 GD_TRY(dump(it + 1));
             }
-            GD_TRY(launch_scale_by_alpha(out + o, ws.x, ac, nb, llh == GD_LLH_POISSON, st));     // Unrolled_ADMM.py:215
+            GD_TRY(launch_scale_by_alpha(out + o, ws.x, ac, nb, llh == GD_LLH_POISSON || (u_v0_over_alpha & 2), st));     // Unrolled_ADMM.py:215 / ADMMNet.py:129     // Unrolled_ADMM.py:215
         }
     }
     return GD_OK;

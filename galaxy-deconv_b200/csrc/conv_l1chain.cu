@@ -1,7 +1,7 @@
 // Level-0 chain kernels of the ResUNet denoiser (32 channels at 48x48, models/ResUNet.py:31-32 and :38-39), tcgen05 path:
 //
 //   DOWN:  x1 = m_head(t);  x = ResBlock(ResBlock(x1))                  -> space-to-depth copy for the m_down1 strided conv
-//   UP:    x  = ResBlock(ResBlock(convT output, hi/lo from HBM))        -> per-tap m_tail partial sums (k_tail_gather)
+//   UP:    x  = ResBlock(ResBlock(m_up1's transposed conv of the level-1 map))  -> per-tap m_tail partial sums (k_tail_gather)
 //
 // i.e. FOUR 3x3 convolutions (two `x + conv(ReLU(conv(x)))` blocks, models/resnet_basicblock.py:69-71) per launch with every
 // intermediate on chip.  Why: at this level one conv per launch is HBM-bound (768 MB per 32-channel fp16 map of 5000 stamps) and
@@ -67,16 +67,27 @@ constexpr int LC_HEAD_TILES = 11;
 constexpr int LC_SR = 304;                           // rows per chunk plane of the space-to-depth operand (12 coarse rows x 25 = 300 used)
 constexpr int LC_WD_BYTES = 4 * LC_C * 2 * LC_C * 2; // 16,384: packed strided-conv weights [16][64][8]
 constexpr int LC_DN = 2 * LC_C;                      // 64 output channels
+// UP: the m_up1 transposed conv (k2 s2, 64 -> 32 channels; models/resnet_basicblock.py:81-87) runs in the same kernel: the 14 coarse
+// rows x 25 of the level-1 map the item needs are bulk-copied over the (then idle) first two T planes, three M128 N128 K64 GEMM
+// tiles (N = 4 sub-pixels x 32 channels) go to TMEM columns [0, 384), and their epilogue scatters hi = rn16(x) into the X planes
+// and lo = rn16(x - hi) into a per-CTA global scratch (L2-resident, 88 KB) from which the helpers build the fp32 stream
+// -- the accumulator's lanes are coarse pixels, the stream's lanes fine rows, so the fp32 values have to change lanes somewhere.
+constexpr int LC_AR = 352;                           // rows per chunk plane of the transposed conv's A operand (350 used)
+constexpr int LC_A_BYTES = 8 * LC_AR * 16;           // 45,056
+constexpr int LC_WU_BYTES = 2 * LC_C * 4 * LC_C * 2; // 16,384: packed transposed-conv weights [8][128][8], n = (dy*2+dx)*32 + co
+constexpr int LC_SCRATCH_BYTES = LC_ROWS * 64;       // per CTA: lo halves of the transposed conv's output, [row][32] fp16
 
 enum { LCB_W_FULL = 0, LCB_W_EMPTY = 2, LCB_ACC_FULL = 4, LCB_ACC_EMPTY = 6, LCB_X_FULL = 8, LCB_T_FULL = 9, LCB_X_FREE = 10,
        LCB_T_FREE = 11, LCB_ITEM_DONE = 12, LCB_X_READY = 13, LCB_TILE_DONE = LCB_X_READY + LC_HEAD_TILES, LCB_S_READY = LCB_TILE_DONE + 4 * 11,
-       LCB_TWIN_FULL = LCB_S_READY + LC_STREAM_TILES, LCB_TWIN_EMPTY, LCB_DOWN_FULL, LCB_DOWN_EMPTY, LCB_COUNT };
+       LCB_TWIN_FULL = LCB_S_READY + LC_STREAM_TILES, LCB_TWIN_EMPTY, LCB_DOWN_FULL, LCB_DOWN_EMPTY, LCB_CONVT_FULL, LCB_CONVT_DONE, LCB_COUNT };
 
 struct L1ChainParams {
     int nb;                        // stamps
     Geom g0, g1;                   // level 0 (48x48) and level 1 (24x24) geometry of the chunk
     const float* t;                // DOWN: scaled denoiser input [nb][48*48]
-    const void *x_hi, *x_lo;       // UP: fp16 hi/lo planes of the m_up1 transposed-conv output [4][g0.Ptot][8]
+    const void* x_in;              // UP: fp16 level-1 map (input of m_up1's transposed conv) [8][g1.Ptot][8]
+    const void* wup;               // UP: packed transposed-conv weights [8][128][8]
+    unsigned char* scratch;        // UP: gridDim.x * LC_SCRATCH_BYTES of global scratch (zero-initialised once: pad rows are never written)
     const void* w[4];              // packed 3x3 weights [tap][4][32][8]: block 1 conv 1, conv 2, block 2 conv 1, conv 2
     const void* wdown;             // DOWN: packed strided-conv weights [16][64][8] (K = (dy*2+dx)*32 + ci)
     float* skip32;                 // DOWN: x2 fp32 [16][g1.Ptot][4] (U-Net skip + residual of the next level)
@@ -134,6 +145,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
         for (int j = 0; j < LC_HEAD_TILES; ++j) mbar_init(bar(LCB_X_READY + j), 4);
         for (int j = 0; j < 44; ++j) mbar_init(bar(LCB_TILE_DONE + j), 4);
         mbar_init(bar(LCB_DOWN_FULL), LC_J); mbar_init(bar(LCB_DOWN_EMPTY), 8);
+        mbar_init(bar(LCB_CONVT_FULL), LC_J); mbar_init(bar(LCB_CONVT_DONE), 8);
         for (int j = 0; j < LC_STREAM_TILES; ++j) mbar_init(bar(LCB_S_READY + j), 4);
         mbar_init(bar(LCB_TWIN_FULL), 1); mbar_init(bar(LCB_TWIN_EMPTY), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -154,7 +166,9 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
     const int total_items = 2 * p.nb;
     const int n_my = total_items > (int)blockIdx.x ? (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const uint32_t Ptot0 = (uint32_t)p.g0.Ptot;
-    constexpr int NLAYERS = MODE == 0 ? 5 : 4;
+    constexpr int NLAYERS = 5;                    // weight layers per item: DOWN: conv 0-3, strided conv; UP: transposed conv, conv 0-3
+    constexpr int L0_IDX = MODE == 0 ? 0 : 1;     // position of conv 0 in that sequence
+    unsigned char* scratch = MODE == 1 ? p.scratch + (size_t)blockIdx.x * LC_SCRATCH_BYTES : nullptr;
     // byte offset of row s of plane pl inside the activation region
     auto row_off = [](int pl, int s) { return (uint32_t)((pl * LC_PSTRIDE + LC_GAP + s) * 16); };
 
@@ -202,39 +216,37 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
     if (warp == 0) {
         // ===== producer =====
         if (lane == 0) {
-            // weight layers of an item: the four 3x3 convs (+ the strided conv, DOWN); layer counter Lc picks the slot
-            auto load_w = [&](int k, int L) {
-                const int Lc = NLAYERS * k + L, slot = Lc & 1;
-                const uint32_t bytes = L < 4 ? (uint32_t)LC_W_BYTES : (uint32_t)LC_WD_BYTES;
+            // weight layers of an item (NLAYERS = 5): layer counter Lc picks the slot.  idx = position in the item's sequence
+            auto load_w = [&](int k, int idx, const void* srcp, uint32_t bytes) {
+                const int Lc = NLAYERS * k + idx, slot = Lc & 1;
                 mbar_wait(bar(LCB_W_EMPTY + slot), ((Lc >> 1) & 1) ^ 1);
                 mbar_expect_tx(bar(LCB_W_FULL + slot), bytes);
                 const uint32_t dst = smem_u32(w_smem) + (uint32_t)slot * LC_W_BYTES;
-                const unsigned char* src = reinterpret_cast<const unsigned char*>(L < 4 ? p.w[L] : p.wdown);
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(srcp);
                 bulk_g2s(dst, src, bytes / 2, bar(LCB_W_FULL + slot));
                 bulk_g2s(dst + bytes / 2, src + bytes / 2, bytes / 2, bar(LCB_W_FULL + slot));
             };
-            auto load_act = [&](int it, const void* src, int pl0, uint32_t full) {
-                const int b = it >> 1, h = it & 1;
-                const size_t row0 = (size_t)p.g0.base0 + (size_t)b * p.g0.S + (size_t)h * (LC_BOT_Y0 * LC_WP);
-                mbar_expect_tx(full, 4u * LC_ROWS * 16u);
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
-                    bulk_g2s(smem_u32(smem) + row_off(pl0 + ch, 0), reinterpret_cast<const unsigned char*>(src) + ((size_t)ch * Ptot0 + row0) * 16,
-                             (uint32_t)LC_ROWS * 16u, full);
-            };
             for (int k = 0; k < n_my; ++k) {
                 const int it = (int)blockIdx.x + k * (int)gridDim.x;
-                if (MODE == 1) { mbar_wait(bar(LCB_X_FREE), (k & 1) ^ 1); load_act(it, p.x_hi, 0, bar(LCB_X_FULL)); }
                 if (MODE == 0) {       // 29 image rows of the 1-channel input: rows 0..28 (top item) or 19..47 (bottom item)
                     mbar_wait(bar(LCB_TWIN_EMPTY), (k & 1) ^ 1);
                     mbar_expect_tx(bar(LCB_TWIN_FULL), (uint32_t)LC_TWIN_BYTES);
                     bulk_g2s(smem_u32(twin), p.t + (size_t)(it >> 1) * NPIX + (size_t)((it & 1) ? (LC_BOT_Y0 - 1) * STAMP : 0), (uint32_t)LC_TWIN_BYTES,
                              bar(LCB_TWIN_FULL));
+                    for (int L = 0; L < 4; ++L) load_w(k, L, p.w[L], (uint32_t)LC_W_BYTES);
+                    load_w(k, 4, p.wdown, (uint32_t)LC_WD_BYTES);
+                } else {
+                    load_w(k, 0, p.wup, (uint32_t)LC_WU_BYTES);
+                    // A operand of the transposed conv: coarse rows [0, 14) (top) / [10, 24) (bottom) of the stamp's level-1 map -> T planes
+                    mbar_wait(bar(LCB_T_FREE), (k & 1) ^ 1);                     // the previous item's 4th conv has finished reading T
+                    const size_t row0 = (size_t)p.g1.base0 + (size_t)(it >> 1) * p.g1.S + (size_t)((it & 1) ? 250 : 0);
+                    mbar_expect_tx(bar(LCB_T_FULL), 8u * 350u * 16u);
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch)
+                        bulk_g2s(smem_u32(smem) + row_off(4, 0) + (uint32_t)(ch * LC_AR * 16),
+                                 reinterpret_cast<const unsigned char*>(p.x_in) + ((size_t)ch * p.g1.Ptot + row0) * 16, 350u * 16u, bar(LCB_T_FULL));
+                    for (int L = 0; L < 4; ++L) load_w(k, 1 + L, p.w[L], (uint32_t)LC_W_BYTES);
                 }
-                load_w(k, 0);
-                if (MODE == 1) { mbar_wait(bar(LCB_T_FREE), (k & 1) ^ 1); load_act(it, p.x_lo, 4, bar(LCB_T_FULL)); }
-                load_w(k, 1); load_w(k, 2); load_w(k, 3);
-                if (MODE == 0) load_w(k, 4);
             }
         }
     } else if (warp <= LC_J) {
@@ -251,13 +263,35 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
             const int it = (int)blockIdx.x + k * (int)gridDim.x, h = it & 1;
             const uint32_t kp = (uint32_t)(k & 1);
             if (MODE == 0) mbar_wait(bar(LCB_DOWN_EMPTY), kp ^ 1);       // the previous item's strided-conv accumulators have been read
+            if (MODE == 1) {
+                // ---- transposed conv: tile jw = coarse rows [128 jw, +128) of the item's window, D = 128 columns at 128 jw ----
+                const int Lc = NLAYERS * k, slot = Lc & 1;
+                mbar_wait(bar(LCB_ITEM_DONE), kp ^ 1);                   // TMEM (stream + accumulators) of the previous item is free
+                mbar_wait(bar(LCB_W_FULL + slot), (Lc >> 1) & 1);
+                mbar_wait(bar(LCB_T_FULL), kp);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t dd = tmem + (uint32_t)(jw * 4 * LC_C);
+                    const uint64_t ad = smem_desc(smem_u32(smem) + row_off(4, 0), LC_AR * 16, 128) + (uint64_t)(uint32_t)(jw * MTILE);
+                    const uint64_t bd = smem_desc(smem_u32(w_smem) + (uint32_t)slot * LC_W_BYTES, 4 * LC_C * 16, 128);
+                    const uint32_t idu = instr_desc_f16(MTILE, 4 * LC_C);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (ks == 0) tc_mma_f16(dd, ad, bd, idu, 0u);
+                        else tc_mma_f16_acc(dd, ad + (uint64_t)(ks * 2 * LC_AR), bd + (uint64_t)(ks * 2 * 4 * LC_C), idu);
+                    }
+                    tc_commit(bar(LCB_CONVT_FULL));
+                    tc_commit(bar(LCB_W_EMPTY + slot));
+                }
+                __syncwarp();
+                mbar_wait(bar(LCB_CONVT_DONE), kp);                      // X holds hi(x), the accumulator columns have been read
+            }
             for (int L = 0; L < 4; ++L) {
-                const int Lc = NLAYERS * k + L, slot = Lc & 1;
+                const int Lc = NLAYERS * k + L0_IDX + L, slot = Lc & 1;
                 mbar_wait(bar(LCB_W_FULL + slot), (Lc >> 1) & 1);
                 const int n = lc_ntiles(L), nprev = L == 0 ? LC_HEAD_TILES : lc_ntiles(L - 1);
                 const int src_pl = (L & 1) ? 4 : 0;       // conv 1 of a block reads X, conv 2 reads T
                 int pw = 0;
-                if (MODE == 1 && L == 0) mbar_wait(bar(LCB_X_FULL), kp);
                 for (int u0 = 0; u0 < n; u0 += LC_J, ++g) {
                     const int i = u0 + jw;
                     const bool active = i < n;
@@ -360,17 +394,16 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(LCB_TWIN_EMPTY));
             } else {
-                mbar_wait(bar(LCB_ITEM_DONE), kp ^ 1);
-                mbar_wait(bar(LCB_X_FULL), kp);
-                mbar_wait(bar(LCB_T_FULL), kp);
+                mbar_wait(bar(LCB_CONVT_DONE), kp);                      // hi in X, lo in the scratch; TMEM columns of the stream are free
                 tc_fence_after();
                 for (int i = 0; i < LC_STREAM_TILES; ++i) {
                     const int s = lc_stream_start(h, i) + q * 32 + lane;
+                    const uint4* lop = reinterpret_cast<const uint4*>(scratch + (size_t)s * 64);
                     uint32_t u[LC_C];
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch) {
                         const uint4 hi = *reinterpret_cast<const uint4*>(smem + row_off(ch, s));
-                        const uint4 lo = *reinterpret_cast<const uint4*>(smem + row_off(4 + ch, s));
+                        const uint4 lo = __ldcg(lop + ch);
                         const float2 f0 = hilo_pair(hi.x, lo.x), f1 = hilo_pair(hi.y, lo.y), f2 = hilo_pair(hi.z, lo.z), f3 = hilo_pair(hi.w, lo.w);
                         u[8 * ch] = __float_as_uint(f0.x); u[8 * ch + 1] = __float_as_uint(f0.y); u[8 * ch + 2] = __float_as_uint(f1.x); u[8 * ch + 3] = __float_as_uint(f1.y);
                         u[8 * ch + 4] = __float_as_uint(f2.x); u[8 * ch + 5] = __float_as_uint(f2.y); u[8 * ch + 6] = __float_as_uint(f3.x); u[8 * ch + 7] = __float_as_uint(f3.y);
@@ -380,7 +413,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
                     tc_st_wait();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(bar(LCB_X_READY + i)); mbar_arrive(bar(LCB_S_READY + i)); }   // the lo rows of stream tile i may be overwritten (T)
+                    if (lane == 0) mbar_arrive(bar(LCB_S_READY + i));
                 }
             }
         }
@@ -392,6 +425,52 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
         for (int k = 0; k < n_my; ++k) {
             const int it = (int)blockIdx.x + k * (int)gridDim.x, bst = it >> 1, h = it & 1;
             const uint32_t kp = (uint32_t)(k & 1);
+            if (MODE == 1) {
+                // ---- transposed-conv epilogue: warp (q, grp) takes sub-pixel row dy = grp (both dx) of coarse rows 128 j + 32 q + lane ----
+                mbar_wait(bar(LCB_CONVT_FULL), kp);
+                tc_fence_after();
+                if (q == 0 && grp == 0) {
+                    // the A operand overwrote pad pixels and gap rows of T planes 4-5 (bytes [0, 45056) from plane 4): restore the zeros
+                    for (int i = lane; i < 128; i += 32) {
+                        int pl, s;
+                        if (i < 28) { pl = 4; s = i * LC_WP + STAMP; }
+                        else if (i < 84) { pl = 4; s = LC_ROWS + (i - 28); }
+                        else if (i < 112) { pl = 5; s = (i - 84) * LC_WP + STAMP; }
+                        else { pl = 5; s = LC_ROWS + (i - 112); }
+                        *reinterpret_cast<uint4*>(smem + row_off(pl, s)) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+                for (int j = 0; j < 3; ++j) {
+                    const int cr = j * MTILE + q * 32 + lane, cy = cr / 25, cx = cr - cy * 25;
+                    const bool valid = cr < 350 && cx < 24;
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx) {
+                        const uint32_t a = tmem + lane_base + (uint32_t)(j * 4 * LC_C + (grp * 2 + dx) * LC_C);
+                        uint32_t d0[16], d1[16];
+                        tc_ld16_nowait(a, d0); tc_ld16_nowait(a + 16, d1);
+                        const int s = (2 * cy + grp) * LC_WP + 2 * cx + dx;
+                        tc_ld_wait16(d0); tc_ld_wait16(d1);
+                        if (valid) {
+                            float v[LC_C];
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) { v[c] = __uint_as_float(d0[c]); v[16 + c] = __uint_as_float(d1[c]); }
+                            uint4* lop = reinterpret_cast<uint4*>(scratch + (size_t)s * 64);
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch) {
+                                uint4 hi, lo;
+                                split8_hilo(v + 8 * ch, hi, lo);
+                                *reinterpret_cast<uint4*>(smem + row_off(ch, s)) = hi;
+                                __stcg(lop + ch, lo);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(LCB_CONVT_DONE));
+            }
             for (int L = 0; L < 4; ++L) {
                 const int n = lc_ntiles(L);
                 for (int u0 = 0; u0 < n; u0 += LC_J, ++g) {
@@ -428,12 +507,6 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
                         for (int c = 0; c < 16; ++c) { v[c] = __uint_as_float(r0[c]); v[16 + c] = __uint_as_float(r1[c]); }
                         if (!(L & 1)) {
                             // first conv of a block: ReLU -> fp16 -> T
-                            if (MODE == 1 && L == 0) {       // T still holds the lo halves until the helpers have moved them into the stream
-                                for (int si = 0; si < LC_STREAM_TILES; ++si) {
-                                    const int ss = lc_stream_start(h, si);
-                                    if (ss < r + MTILE && ss + MTILE > r) mbar_wait(bar(LCB_X_READY + si), kp);
-                                }
-                            }
                             if (wr) {
 #pragma unroll
                                 for (int c = 0; c < LC_C; ++c) v[c] = fmaxf(v[c], 0.f);
@@ -554,7 +627,7 @@ static int l1chain_launch(int mode, const L1ChainParams& p, const float* head_w,
     const int items = 2 * p.nb, grid = items < g_lc_sms ? items : g_lc_sms;
     cudaEvent_t e1 = nullptr;
     double flops = 4.0 * 2.0 * (double)p.nb * NPIX * (double)LC_C * LC_C * 9;            // four 3x3 convs, valid pixels
-    if (mode == 0) flops += 2.0 * (double)p.nb * (NPIX / 4) * (4.0 * LC_C) * LC_DN;      // + the k2s2 strided conv
+    flops += 2.0 * (double)p.nb * (NPIX / 4) * (4.0 * LC_C) * LC_DN;                     // + the k2s2 strided (DOWN) / transposed (UP) conv
     { int rc = conv_profile_mark(flops, st, &e1); if (rc != GD_OK) return rc; }
     if (mode == 0) k_l1_chain<0><<<grid, LC_THREADS, LC_SMEM, st>>>(p, hw);
     else k_l1_chain<1><<<grid, LC_THREADS, LC_SMEM, st>>>(p, hw);
@@ -573,13 +646,16 @@ int launch_l1chain_down(const Geom& g0, const Geom& g1, int nb, const float* t, 
     return l1chain_launch(0, p, head_w_host, nullptr, st);
 }
 
-int launch_l1chain_up(const Geom& g0, const Geom& g1, int nb, const void* x_hi, const void* x_lo, const float* tail_w_host, const void* const* w4,
-                      float* tail_part, cudaStream_t st) {
+size_t l1chain_scratch_bytes() { return (size_t)160 * LC_SCRATCH_BYTES; }     // one region per CTA of the persistent grid (<= 160 SMs)
+
+int launch_l1chain_up(const Geom& g0, const Geom& g1, int nb, const void* x_in, const void* wup, const float* tail_w_host, const void* const* w4,
+                      float* tail_part, void* scratch, cudaStream_t st) {
     L1ChainParams p;
     memset(&p, 0, sizeof(p));
-    p.nb = nb; p.g0 = g0; p.g1 = g1; p.x_hi = x_hi; p.x_lo = x_lo; p.tail_part = tail_part;
+    p.nb = nb; p.g0 = g0; p.g1 = g1; p.x_in = x_in; p.wup = wup; p.tail_part = tail_part; p.scratch = reinterpret_cast<unsigned char*>(scratch);
     for (int i = 0; i < 4; ++i) p.w[i] = w4[i];
-    if (!x_hi || !x_lo || !tail_w_host || !tail_part) { set_error("conv_l1chain: up needs the hi/lo stream, the tail weights and tail_part"); return GD_EBADSHAPE; }
+    if (!x_in || !wup || !tail_w_host || !tail_part || !scratch) { set_error("conv_l1chain: up needs the level-1 map, the transposed-conv / tail weights, tail_part and the scratch"); return GD_EBADSHAPE; }
+    if (g_lc_sms > 160) { set_error("conv_l1chain: scratch is sized for 160 CTAs"); return GD_EUNSUPPORTED; }
     return l1chain_launch(1, p, nullptr, tail_w_host, st);
 }
 

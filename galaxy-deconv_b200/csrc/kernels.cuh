@@ -16,8 +16,9 @@ int conv_rb_init();
 int conv_l1chain_init();
 int launch_l1chain_down(const Geom& g0, const Geom& g1, int nb, const float* t, const float* head_w_host, const void* const* w4, const void* wdown,
                         float* skip32, void* x2_16, cudaStream_t st);
-int launch_l1chain_up(const Geom& g0, const Geom& g1, int nb, const void* x_hi, const void* x_lo, const float* tail_w_host, const void* const* w4,
-                      float* tail_part, cudaStream_t st);
+size_t l1chain_scratch_bytes();
+int launch_l1chain_up(const Geom& g0, const Geom& g1, int nb, const void* x_in, const void* wup, const float* tail_w_host, const void* const* w4,
+                      float* tail_part, void* scratch, cudaStream_t st);
 bool conv_rb_supported(const ConvParams& p1, const ConvParams& p2);
 int launch_conv_rb(const ConvParams& p1, const ConvParams& p2, cudaStream_t st);
 

@@ -182,30 +182,105 @@ def pack_state_dict(state_dict, arch, n_iters, precision, device) -> _Packed:
     return _Packed(out, device)
 
 
+def graph_max_batch() -> int:
+    """Batches up to this size run as ONE replayed CUDA graph (env GDECONV_GRAPH_MAX, 0 disables): a forward pass is ~300 kernel
+    launches, which dominate the latency of a single galaxy (BASELINE config 1, tutorials/deconv_cpu.ipynb cell 7)."""
+    try:
+        return max(0, int(os.environ.get('GDECONV_GRAPH_MAX', '64')))
+    except ValueError:
+        return 64
+
+
 class AdmmEngine:
     """Per-module cache of packed weights + the forward calls.  The module's parameters stay the source of truth:
-    the pack is redone whenever a parameter/buffer is replaced (load_state_dict, .to(device)) or modified in place."""
+    the pack is redone whenever a parameter/buffer is replaced (load_state_dict, .to(device)) or modified in place
+    (``_version`` bump).  Updates that bypass autograd's version counter (``param.data.copy_()``) need ``invalidate()``."""
 
     def __init__(self, module, arch, n_iters):
         self._module = module
         self.arch, self.n_iters = arch, n_iters
         self._packed = {}        # (device index, precision) -> (signature, _Packed)
+        self._tensors = None     # cached list of the module's parameter / buffer tensors (the signature walks it, not state_dict())
+        self._graphs = {}        # (device index, precision, llh, v0, B) -> captured forward
+
+    # engines hold ctypes handles and CUDA graphs: copies / pickles of the owning module start with an empty cache
+    def __deepcopy__(self, memo):
+        return AdmmEngine(self._module, self.arch, self.n_iters)
+
+    def __getstate__(self):
+        return dict(_module=self._module, arch=self.arch, n_iters=self.n_iters)
+
+    def __setstate__(self, st):
+        self.__init__(st['_module'], st['arch'], st['n_iters'])
+
+    def invalidate(self):
+        """Drop packed weights and captured graphs (call after in-place updates through ``.data``, which do not bump ``_version``)."""
+        self._packed.clear()
+        self._graphs.clear()
+        self._tensors = None
 
     def _signature(self):
-        sd = self._module.state_dict(keep_vars=True)
-        return tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+        # (data_ptr, _version) of every parameter / buffer.  The tensor list is cached: nn.Module replaces the tensor OBJECTS on
+        # load_state_dict(assign=True) / .to(device) of parameters only through _parameters / _buffers, whose identity we check.
+        m = self._module
+        ts = self._tensors
+        if ts is None or not hasattr(m, 'parameters'):
+            sd = m.state_dict(keep_vars=True)
+            if not hasattr(m, 'parameters'):
+                return tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+            ts = self._tensors = list(sd.values())
+        sig = tuple((v.data_ptr(), v._version) for v in ts)
+        return sig
 
     def weights(self, device, precision):
         key = (device.index, precision)
         sig = self._signature()
         hit = self._packed.get(key)
         if hit is None or hit[0] != sig:
-            hit = (sig, pack_state_dict(self._module.state_dict(), self.arch, self.n_iters, precision, device))
-            self._packed[key] = hit
+            # the cached tensor list may be stale (parameters replaced): rebuild it and compare once more before repacking
+            self._tensors = None
+            sig = self._signature()
+            if hit is None or hit[0] != sig:
+                hit = (sig, pack_state_dict(self._module.state_dict(), self.arch, self.n_iters, precision, device))
+                self._packed[key] = hit
+                self._graphs.clear()
         return hit[1]
 
+    def _graphed(self, w, y, psf, a, llh, v0, precision, ws, nbytes):
+        """Small batches: the whole forward (SubNet, prologue, n x [x-update, ~35 conv launches, tail]) is captured ONCE per
+        (weights, batch size) into a CUDA graph over static buffers and replayed -- three small device copies + one graph launch
+        instead of ~300 kernel launches."""
+        B, dev = y.shape[0], y.device
+        key = (dev.index, precision, llh, int(v0), B, nbytes)
+        g = self._graphs.get(key)
+        cur = torch.cuda.current_stream(dev)
+        if g is None:
+            st = dict(y=torch.empty_like(y), psf=torch.empty_like(psf), a=torch.empty_like(a), out=torch.empty_like(y), ws=ws, w=w)   # ws / w: kept alive
+
+            def run(stream):
+                check(lib.gd_admm_forward(w.handle, llh, int(v0), _ptr(st['y']), _ptr(st['psf']), _ptr(st['a']), _ptr(st['out']),
+                                          None, None, B, _ptr(ws), nbytes, C.c_void_p(stream.cuda_stream)))
+            st['y'].copy_(y); st['psf'].copy_(psf); st['a'].copy_(a)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                run(side)                                   # warm-up outside capture (lazy per-kernel attributes, occupancy queries)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                run(torch.cuda.current_stream(dev))
+            st['graph'], st['launches'] = graph, None
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            g = self._graphs[key] = st
+        g['y'].copy_(y, non_blocking=True); g['psf'].copy_(psf, non_blocking=True); g['a'].copy_(a, non_blocking=True)
+        g['graph'].replay()
+        return g['out'].clone()
+
     def admm(self, y, psf, alpha, llh=_lib.LLH_GAUSSIAN, v0_over_alpha=False, want_rho=False, want_analysis=False,
-             precision=None):
+             precision=None, times_alpha=False):
+        v0_over_alpha = int(bool(v0_over_alpha)) | (2 if times_alpha else 0)          # flag word of gd_admm_forward
         y = require_cuda_stamps('y', y)
         B, dev = y.shape[0], y.device
         psf = require_cuda_stamps('psf', psf, B)
@@ -222,6 +297,8 @@ class AdmmEngine:
                 shape = (self.n_iters, 3, B, 1, STAMP, STAMP) if self.arch == _lib.ARCH_G else (self.n_iters + 1, 5, B, 1, STAMP, STAMP)
                 ana = torch.empty(shape, device=dev)
             chunk = _chunk_for(B, self.arch)
+            if ana is None and rho is None and 0 < B <= graph_max_batch() and not torch.cuda.is_current_stream_capturing():
+                return self._graphed(w, y, psf, a, llh, v0_over_alpha, precision, ws, nbytes), None, None
             if ana is None and B > chunk and n_streams() == 2:
                 # two chunks in flight: even chunks on the caller's stream, odd chunks on the side stream
                 ws2, _ = _workspace(dev, self.arch, _lib.PRECISIONS[precision], chunk, slot=1)
@@ -233,12 +310,12 @@ class AdmmEngine:
                 for i, c0 in enumerate(range(0, B, chunk)):
                     nb = min(chunk, B - c0)
                     st, wsi = (cur, ws) if i % 2 == 0 else (side, ws2)
-                    check(lib.gd_admm_forward(w.handle, llh, int(bool(v0_over_alpha)), _ptr(y[c0:c0 + nb]), _ptr(psf[c0:c0 + nb]),
+                    check(lib.gd_admm_forward(w.handle, llh, int(v0_over_alpha), _ptr(y[c0:c0 + nb]), _ptr(psf[c0:c0 + nb]),
                                               _ptr(a[c0:c0 + nb]), _ptr(out[c0:c0 + nb]), _ptr(rho[c0:c0 + nb]) if rho is not None else None,
                                               None, nb, _ptr(wsi), nbytes, C.c_void_p(st.cuda_stream)))
                 cur.wait_stream(side)
             else:
-                check(lib.gd_admm_forward(w.handle, llh, int(bool(v0_over_alpha)), _ptr(y), _ptr(psf), _ptr(a), _ptr(out),
+                check(lib.gd_admm_forward(w.handle, llh, int(v0_over_alpha), _ptr(y), _ptr(psf), _ptr(a), _ptr(out),
                                           _ptr(rho), _ptr(ana), B, _ptr(ws), nbytes, _stream(dev)))
         return out, rho, ana
 
@@ -258,16 +335,11 @@ class AdmmEngine:
 
     @staticmethod
     def _host_plan(B, cap):
-        """Chunk sizes for a host-resident batch: a short first and last chunk (their H2D / D2H cannot hide behind compute of
-        the same call) around balanced large chunks (long persistent kernels)."""
-        edge = min(1024, cap)
-        if B <= 3 * edge:
-            return [B] if B <= cap else [B - B // 2, B // 2]
-        mid = B - 2 * edge
-        n = max(1, -(-mid // cap))
-        per = -(-mid // n)
-        sizes = [edge] + [min(per, mid - i * per) for i in range(n)] + [edge]
-        return [v for v in sizes if v > 0]
+        """Chunk sizes for a host-resident batch: the fewest balanced chunks that fit the workspace (long persistent kernels).  In
+        a loop of calls the first chunk's H2D and the last chunk's D2H overlap the neighbouring calls' compute (copy streams)."""
+        parts = max(1, -(-B // cap))
+        per = -(-B // parts)
+        return [min(per, B - i * per) for i in range(parts) if B - i * per > 0]
 
     def admm_host(self, y, psf, alpha, out=None, want_e=True, device=None, precision=None):
         """model(y, psf, alpha) for a batch that lives in (pinned) HOST memory: the batch is cut into chunks and chunk k+1's

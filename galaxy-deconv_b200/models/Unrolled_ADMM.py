@@ -90,19 +90,36 @@ class Unrolled_ADMM(nn.Module):
         return out                                   # x_list[-1] (* alpha for Poisson), :215
 
 
+class _OnesRho:
+    """state_dict view + the constant rho vectors of Unrolled_ADMM_Old(SubNet=False) (they are not part of its state_dict)"""
+
+    def __init__(self, module, n):
+        self._m, self._n = module, n
+
+    def state_dict(self, keep_vars=False):
+        sd = dict(self._m.state_dict(keep_vars=keep_vars))
+        sd['rho1_iters'] = torch.ones(self._n)
+        sd['rho2_iters'] = torch.ones(self._n)
+        return sd
+
+
 class Unrolled_ADMM_Old(nn.Module):
     def __init__(self, n_iters=8, llh='Poisson', denoiser='ResUNet', PnP=True, SubNet=True):
         super().__init__()
         _check(denoiser, PnP)
-        if not SubNet:
-            raise NotImplementedError('gdeconv: Unrolled_ADMM_Old needs SubNet=True (its rho vectors are not parameters, :385-386)')
         self.n, self.llh, self.PnP, self.SubNet, self.denoiser = n_iters, llh, PnP, SubNet, denoiser
         self.X = X_Update()
         self.V = V_Update_Poisson() if llh == 'Poisson' else V_Update_Gaussian()
         self.Z = Z_Update_ResUNet()
-        self.init = InitNet(self.n)
         self.precision = None
-        self._engine = [AdmmEngine(self, _lib.ARCH_U, n_iters)]
+        if self.SubNet:
+            self.init = InitNet(self.n)
+            self._engine = [AdmmEngine(self, _lib.ARCH_U, n_iters)]
+        else:
+            # :385-386: plain tensors of ones (NOT parameters, absent from the state_dict): rho1 = rho2 = 1 in every iteration
+            self.rho1_iters = torch.ones(size=[self.n, ])
+            self.rho2_iters = torch.ones(size=[self.n, ])
+            self._engine = [AdmmEngine(_OnesRho(self, n_iters), _lib.ARCH_U, n_iters)]
 
     def forward(self, y, kernel, alpha):
         llh = _lib.LLH_POISSON if self.llh == 'Poisson' else _lib.LLH_GAUSSIAN

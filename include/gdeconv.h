@@ -83,7 +83,9 @@ GD_API int gd_workspace_init(void* workspace, size_t bytes, int arch, int precis
  *   analysis optional per-iteration state:
  *            G: [n_iters][3][batch][2304]  (x, z, u)                 (analysis=True lists, :147-152)
  *            U: [n_iters+1][5][batch][2304] (v, z, x, u1, u2), entry 0 = initial state (Old, :419-442)
- *   u_v0_over_alpha  path U only: initial v = y/alpha (Unrolled_ADMM_Old, :416) instead of y (:194)
+ *   u_v0_over_alpha  path U only, bit flags: bit 0: initial v = y/alpha (Unrolled_ADMM_Old, :416) instead of y (:194);
+ *                    bit 1: the result is multiplied by alpha for BOTH likelihoods (models/ADMMNet.py:129 -- with
+ *                    rho1_iters = rho2_iters = 0.5 in the weights this entry point is ADMMNet.forward, :96-129)
  * Any `batch` >= 0 is accepted; it is processed in chunks of the workspace's `chunk`. */
 GD_API int gd_admm_forward(const GdWeights* w, int llh, int u_v0_over_alpha, const float* y, const float* psf,
                     const float* alpha, float* out, float* rho_out, float* analysis, int batch, void* workspace,

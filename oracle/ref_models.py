@@ -302,10 +302,32 @@ class Unrolled_ADMM_Old(Unrolled_ADMM):
 
     def __init__(self, n_iters=8, llh='Poisson', denoiser='ResUNet', PnP=True, SubNet=True):
         super().__init__(n_iters, llh, denoiser, PnP, subnet=SubNet)
+        if not SubNet:
+            # :385-386: plain tensors of ones, NOT parameters (absent from the state_dict)
+            del self.rho1_iters, self.rho2_iters
+            self.rho1_iters, self.rho2_iters = torch.ones(n_iters), torch.ones(n_iters)
 
     def forward(self, y, kernel, alpha):
         L = self._iterate(y, kernel, alpha, v0_over_alpha=True)
         return L['v'], L['z'], L['x'], L['u1'], L['u2'], alpha
+
+
+class ADMMNet(Unrolled_ADMM):
+    """models/ADMMNet.py:78-129 -- the fixed-rho ablation: rho1 = rho2 = 0.5 (:117-118), the same X / V / Z updates and
+    init_l2 as Unrolled_ADMM (:12-37, :88-94), v initialised to the clamped y (:109), denoiser weights read from ``model_file``
+    (:48-61), and the result multiplied by alpha for BOTH likelihoods (:129)."""
+
+    def __init__(self, n_iters=8, llh='Poisson', denoiser='ResUNet', PnP=True, model_file=None):
+        super().__init__(n_iters, llh, denoiser, PnP, subnet=False)
+        del self.rho1_iters, self.rho2_iters
+        self.rho1_iters, self.rho2_iters = torch.full((n_iters,), 0.5), torch.full((n_iters,), 0.5)
+        try:
+            self.Z.net.load_state_dict(torch.load(model_file, map_location='cpu'))
+        except Exception:
+            raise ValueError('Please provide a valid model file for ResUNet denoiser.')
+
+    def forward(self, y, kernel, alpha):
+        return self._iterate(y, kernel, alpha, v0_over_alpha=False)['x'][-1] * alpha
 
 
 # --------------------------------------------------------------------------

@@ -1,6 +1,6 @@
 """The drop-in boundary drops in: with galaxy-deconv_b200/ AHEAD of the
 reference checkout on sys.path, the modules of the hot path resolve to this package and every other reference module
-(utils.utils_data, utils.utils_test, models.ADMMNet, ...) still resolves to the reference's own file, because ``models`` and
+(utils.utils_data, utils.utils_test, utils.utils_deblur, ...) still resolves to the reference's own file, because ``models`` and
 ``utils`` are namespace packages here exactly as they are in the reference.
 
 CPU part: import resolution (in a subprocess with a clean sys.path; fpfs is stubbed because it is not installable here) and
@@ -64,10 +64,10 @@ import models.ADMMNet
 import utils.utils_data, utils.utils_test, utils.utils_torch
 mine = lambda m: os.path.realpath(m.__file__).startswith(os.path.realpath(pkg))
 theirs = lambda m: os.path.realpath(m.__file__).startswith(os.path.realpath(ref))
-assert all(mine(sys.modules[n]) for n in ('models.Richard_Lucy', 'models.Tikhonet', 'models.Unrolled_ADMM', 'models.Wiener',
+import utils.utils_deblur                                           # a reference-only helper module (scipy): must stay importable
+assert all(mine(sys.modules[n]) for n in ('models.Richard_Lucy', 'models.Tikhonet', 'models.Unrolled_ADMM', 'models.Wiener', 'models.ADMMNet',
                                           'models.unrolled_admm_gaussian', 'utils.utils_torch')), 'hot-path modules must come from this package'
-assert all(theirs(sys.modules[n]) for n in ('utils.utils_data', 'utils.utils_test', 'models.ADMMNet')), 'other modules must stay the reference files'
-assert models.ADMMNet.psf_to_otf is psf_to_otf                      # the reference's ADMMNet now runs on this package's helpers
+assert all(theirs(sys.modules[n]) for n in ('utils.utils_data', 'utils.utils_test', 'utils.utils_deblur')), 'other modules must stay the reference files'
 print('DROPIN-OK')
 '''
 

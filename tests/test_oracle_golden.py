@@ -90,6 +90,36 @@ def test_survey_known_answers():
     assert abs(float(out.sum()) - 55.3592) < 0.02 and abs(float(out.abs().mean()) - 0.121897) < 1e-4
 
 
+def test_admmnet_and_old_without_subnet(tmp_path):
+    """oracle ADMMNet (models/ADMMNet.py:78-129) and Unrolled_ADMM_Old(SubNet=False) (:385-386) vs the outputs of the REAL reference
+    (tests/golden/make_golden_admmnet.py, bit-exact at generation time)"""
+    g = torch.load(os.path.join(ROOT, 'tests', 'golden', 'golden_v1.pt'))
+    ga = torch.load(os.path.join(ROOT, 'tests', 'golden', 'admmnet_v1.pt'))
+    y, k, a = (t[:2] for t in _inputs(g))
+    torch.manual_seed(ga['seeds']['net'])
+    f = str(tmp_path / 'resunet.pth')
+    torch.save(O.ResUNet().state_dict(), f)
+    for llh in ('Gaussian', 'Poisson'):
+        with torch.no_grad():
+            out = O.ADMMNet(2, llh=llh, model_file=f).eval()(y, k, a)
+        assert rel_l2(out, ga['out'][f'ADMMNet2_{llh}']).max() < TOL
+    with pytest.raises(ValueError):
+        O.ADMMNet(2, model_file=str(tmp_path / 'missing.pth'))
+    m = O.Unrolled_ADMM_Old(2, llh='Gaussian', SubNet=False).eval()
+    m.load_state_dict(O.seeded_state_dict(lambda: O.Unrolled_ADMM_Old(2, llh='Gaussian', SubNet=False), ga['seeds']['old']))
+    with torch.no_grad():
+        lists = m(y, k, a)
+    for got, want in zip([t[-1] for t in lists[:5]], ga['out']['UOld2_norho']):
+        assert rel_l2(got, want).max() < TOL
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='reference checkout not mounted')
+def test_admmnet_golden_vs_live_reference():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'golden', 'make_golden_admmnet.py'), '--check'],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONDONTWRITEBYTECODE='1'))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='reference checkout not mounted')
 def test_oracle_bitexact_vs_live_reference():
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'golden', 'make_golden.py'), '--check'],

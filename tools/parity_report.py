@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Parity margins of the CUDA path against the CPU oracle on synthetic stamps (plus the golden fixtures), per model and
-precision mode -> markdown on stdout (profiles/parity_r01.md)."""
+precision mode -> markdown on stdout (profiles/parity_r02.md)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, 'galaxy-deconv_b200'), ROOT]
 import torch
 import oracle.ref_models as O
 from gdeconv import moments_e
-from gdeconv.synth import make_batch
+from gdsynth import make_batch
 from models.unrolled_admm_gaussian import UnrolledADMMGaussian
 from models.Unrolled_ADMM import Unrolled_ADMM
 from models.Richard_Lucy import Richard_Lucy
@@ -35,6 +35,17 @@ for n, seed in ((2, 11), (4, 13), (8, 12)):
         os.environ['GDECONV_PRECISION'] = prec
         m = UnrolledADMMGaussian(n).eval(); m.load_state_dict(sd); m = m.to(dev)
         row(f'UnrolledADMMGaussian({n})', prec, m(y.to(dev), k.to(dev), a.to(dev)).cpu(), want, '1e-3 / 1e-4')
+# fixed rho (subnet=False), the marginal two-iteration case of tests/test_gpu_parity_wide.py and its four-iteration form
+for n, rho in ((2, [0.7, 1.3]), (4, [0.7, 1.3, 0.9, 1.1])):
+    sd = O.seeded_state_dict(lambda: O.UnrolledADMMGaussian(n, subnet=False), 4)
+    sd['rho_iters'] = torch.tensor(rho)
+    ref = O.UnrolledADMMGaussian(n, subnet=False).eval(); ref.load_state_dict(sd)
+    with torch.no_grad():
+        want = ref(y, k, a)
+    for prec in ('fp16_umma', 'fp16_simt', 'fp32_simt'):
+        os.environ['GDECONV_PRECISION'] = prec
+        m = UnrolledADMMGaussian(n, subnet=False).eval(); m.load_state_dict(sd); m = m.to(dev)
+        row(f'UnrolledADMMGaussian({n}, subnet=False, seed 4)', prec, m(y.to(dev), k.to(dev), a.to(dev)).cpu(), want, '1e-3 / 1e-4')
 nu = min(N, 16)
 for llh, seed in (('Gaussian', 22), ('Poisson', 23)):
     sd = O.seeded_state_dict(lambda: O.Unrolled_ADMM(8, llh=llh), seed)
