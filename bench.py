@@ -258,10 +258,11 @@ def main():
             ach = fl_k.value / (ms_k.value * 1e-3) / 1e12
             traffic, traffic_note = None, 'no ncu capture found under profiles/'
             try:        # DRAM bytes per launch from the committed ncu capture of the same kernel (per launch, like `achieved`)
-                tj = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic_r01.json')))
+                tpath = next(q for q in (os.path.join(ROOT, 'profiles', f) for f in ('roofline_traffic_r02.json', 'roofline_traffic_r01.json')) if os.path.exists(q))
+                tj = json.load(open(tpath))
                 per_chunk = engine._chunk_for(hi - lo)
                 traffic = tj['avg_traffic_bytes_per_launch'] * min(per_chunk, hi - lo) / tj['stamps_per_launch']
-                traffic_note = 'ncu dram__bytes_read+write per tcgen05 conv launch (profiles/roofline_traffic_r01.json), scaled by stamps per launch'
+                traffic_note = 'ncu dram__bytes_read+write per tcgen05 conv launch (profiles/%s), scaled by stamps per launch' % os.path.basename(tpath)
             except Exception:
                 pass
             roof = dict(bound='tensor', achieved=ach, peak=P['tensor_sustained'], unit='TFLOP/s', frac=ach / P['tensor_sustained'], traffic=traffic,
