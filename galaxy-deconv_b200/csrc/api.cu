@@ -194,6 +194,7 @@ static int init_once(int device) {
     GD_TRY(conv_umma_init());
     GD_TRY(conv_rb_init());
     GD_TRY(conv_l1chain_init());
+    GD_TRY(conv_l2chain_init());
     done.fetch_or(1u << device);
     return GD_OK;
 }
@@ -511,6 +512,19 @@ static int g_fuse_ht_fwd();
 static bool l1chain_applies(const GdWeights* W) {
     return l1chain_mode() && W->precision == PREC_FP16_UMMA && W->nc[0] == 32 && g_fuse_ht_fwd() && hilo_mode() && tail_g_mode();
 }
+// Level-1 chain kernel (conv_l2chain.cu): the two ResBlocks of m_down2 resp. m_up2 as one launch each.  GDECONV_L2CHAIN=0 restores the
+// per-conv launches at that level.
+static int g_l2chain = -1;
+static int l2chain_mode() {
+    if (g_l2chain < 0) {
+        const char* e = getenv("GDECONV_L2CHAIN");
+        g_l2chain = e ? atoi(e) : 1;
+    }
+    return g_l2chain;
+}
+static bool l2chain_applies(const GdWeights* W) {
+    return l2chain_mode() && l1chain_applies(W) && W->nc[1] == 64;
+}
 static bool xhead_applies(const GdWeights* W) {
     return xhead_mode() && W->precision == PREC_FP16_UMMA && W->nc[0] == 32 && g_fuse_ht_fwd() && !l1chain_applies(W);
 }
@@ -528,6 +542,7 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
     const bool fuse = prec == PREC_FP16_UMMA && fuse_ht_mode() && C[0] <= 64;
     const bool hilo = prec == PREC_FP16_UMMA && hilo_mode();
     const bool l1chain = l1chain_applies(W);      // level 0 runs in the two chain kernels: no separate head launch, no level-0 fp32 buffers
+    const bool l2chain = l2chain_applies(W);      // the ResBlock pairs of level 1 run in one chain launch each
     if (!l1chain) {   // head (ResUNet.py:31): x1 = conv(t)  -> skip32[0] (fp32) + a16[0]
         ConvParams p = conv_base(g[0], nb);
         p.N = C[0]; p.out32 = fuse ? nullptr : ws.skip32[0]; p.out16 = ws.a16[0];
@@ -600,10 +615,15 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
             const void* w4[4] = {W->down_rb[0][0][0], W->down_rb[0][0][1], W->down_rb[0][1][0], W->down_rb[0][1][1]};
             // ... and the k2s2 strided conv of m_down1 (its space-to-depth operand never leaves shared memory)
             return launch_l1chain_down(g[0], g[1], n, t + (size_t)s0 * NPIX, W->head_h, w4, W->down[0], (float*)at(ws.skip32[1], 1, s0),
-                                       at(ws.a16[1], 1, s0), st);
+                                       at(ws.a16[1], 1, s0), l2chain ? at(ws.lo16[1], 1, s0) : nullptr, st);
         }
-        GD_TRY(resblock_pair(L, s0, n, W->down_rb[L][0], W->down_rb[L][1], ws.skip32[L], ws.p32a[L], ws.a16[L], ws.p32a[L], nullptr,
-                             nullptr, nullptr, ws.d16[L + 1]));
+        if (L == 1 && l2chain) {
+            const void* w4[4] = {W->down_rb[1][0][0], W->down_rb[1][0][1], W->down_rb[1][1][0], W->down_rb[1][1][1]};
+            Geom g2 = g[2]; g2.M = n * g[2].S;
+            GD_TRY(launch_l2chain(0, g[1], g2, n, at(ws.a16[1], 1, s0), at(ws.lo16[1], 1, s0), w4, at(ws.d16[2], 2, s0), nullptr, nullptr, st));
+        } else
+            GD_TRY(resblock_pair(L, s0, n, W->down_rb[L][0], W->down_rb[L][1], ws.skip32[L], ws.p32a[L], ws.a16[L], ws.p32a[L], nullptr,
+                                 nullptr, nullptr, ws.d16[L + 1]));
         ConvParams p = conv_base(g[L + 1], n);         // k2s2 strided conv as a 1-tap GEMM on the space-to-depth copy
         p.ntaps = 1; p.off[0] = 0; p.Kt = 4 * C[L]; p.N = C[L + 1]; p.a = at(ws.d16[L + 1], L + 1, s0); p.w = W->down[L];
         p.out32 = (float*)at(ws.skip32[L + 1], L + 1, s0); p.out16 = at(ws.a16[L + 1], L + 1, s0);
@@ -620,6 +640,11 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         p.out32 = (float*)at(ws.p32a[L], L, s0); p.out16 = at(ws.a16[L], L, s0);
         if (hilo) { p.out_lo = at(ws.lo16[L], L, s0); p.out32 = nullptr; }
         GD_TRY(run_conv(p, prec, st));
+        if (L == 1 && l2chain) {
+            const void* w4[4] = {W->up_rb[1][0][0], W->up_rb[1][0][1], W->up_rb[1][1][0], W->up_rb[1][1][1]};
+            return launch_l2chain(1, g[1], g[2], n, at(ws.a16[1], 1, s0), at(ws.lo16[1], 1, s0), w4, nullptr, (const float*)at(ws.skip32[1], 1, s0),
+                                  at(ws.a16[1], 1, s0), st);
+        }
         if (L > 0) return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L],
                                         ws.skip32[L], nullptr, ws.a16[L], nullptr);
         return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L], ws.skip32[L],

@@ -92,6 +92,7 @@ struct L1ChainParams {
     const void* wdown;             // DOWN: packed strided-conv weights [16][64][8] (K = (dy*2+dx)*32 + ci)
     float* skip32;                 // DOWN: x2 fp32 [16][g1.Ptot][4] (U-Net skip + residual of the next level)
     void* x2_16;                   // DOWN: x2 fp16 [8][g1.Ptot][8] (operand of the next conv)
+    void* x2_lo;                   // DOWN, optional: rn16(x2 - fp16(x2)), same layout (lo half of the stream read by conv_l2chain.cu)
     float* tail_part;              // UP: [9][g0.Ptot] per-tap m_tail partial sums
 };
 struct L1ChainHT { float head[9 * LC_C], tail[9 * LC_C]; };
@@ -588,7 +589,12 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_l1_chain(const L1ChainParams 
 #pragma unroll
                         for (int c4 = 0; c4 < 8; ++c4) o32[(size_t)c4 * g1.Ptot] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
 #pragma unroll
-                        for (int c8 = 0; c8 < 4; ++c8) o16[(size_t)c8 * g1.Ptot] = pack8_half(v + 8 * c8);
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            uint4 hi8, lo8;
+                            split8_hilo(v + 8 * c8, hi8, lo8);
+                            o16[(size_t)c8 * g1.Ptot] = hi8;
+                            if (p.x2_lo) (reinterpret_cast<uint4*>(p.x2_lo) + (size_t)(grp * 4) * g1.Ptot + row)[(size_t)c8 * g1.Ptot] = lo8;
+                        }
                     }
                 }
             }
@@ -637,10 +643,10 @@ static int l1chain_launch(int mode, const L1ChainParams& p, const float* head_w,
 }
 
 int launch_l1chain_down(const Geom& g0, const Geom& g1, int nb, const float* t, const float* head_w_host, const void* const* w4, const void* wdown,
-                        float* skip32, void* x2_16, cudaStream_t st) {
+                        float* skip32, void* x2_16, void* x2_lo, cudaStream_t st) {
     L1ChainParams p;
     memset(&p, 0, sizeof(p));
-    p.nb = nb; p.g0 = g0; p.g1 = g1; p.t = t; p.wdown = wdown; p.skip32 = skip32; p.x2_16 = x2_16;
+    p.nb = nb; p.g0 = g0; p.g1 = g1; p.t = t; p.wdown = wdown; p.skip32 = skip32; p.x2_16 = x2_16; p.x2_lo = x2_lo;
     for (int i = 0; i < 4; ++i) p.w[i] = w4[i];
     if (!t || !head_w_host || !wdown || !skip32 || !x2_16) { set_error("conv_l1chain: down needs t, the head / strided-conv weights and the x2 outputs"); return GD_EBADSHAPE; }
     return l1chain_launch(0, p, head_w_host, nullptr, st);

@@ -1,0 +1,317 @@
+// Level-1 chain kernel of the ResUNet denoiser (64 channels at 24x24, path G: models/ResUNet.py:33 and :37), tcgen05 path:
+// the two ResBlocks of m_down2 resp. m_up2 (four 3x3 convolutions, models/resnet_basicblock.py:69-71) in ONE launch per stage,
+// with every intermediate on chip.  One launch per conv moves the fp16 hi/lo stream through HBM around every ResBlock and
+// runs the residual-carrying second convs at the HBM roofline (5.7 TB/s, profiles/layers_r02.csv); here a work item is ONE
+// WHOLE STAMP (625 padded-linear rows = 5 tiles of 128, no halo to recompute), so HBM sees the stream once per stage.
+//
+//   * the fp16 operand copies of the stream (X) and of ReLU(conv1) (T) live in shared memory: 2 x 8 chunk planes x 672 rows x 16 B;
+//     rows 625..671 of a plane are never written (zero row below the stamp + gap absorbing the tap shifts);
+//   * the residual stream is hi + lo: hi = the operand copy in X, lo = rn16(x - hi) packed two per column in TENSOR MEMORY
+//     (5 tiles x 32 columns) -- |x - (hi + lo)| <= 2^-22 |x| as in the HBM stream of the other levels;
+//   * a conv's weights (74 KB) do not fit beside X and T, so the MMA loop is TAP-OUTER: the five tiles' accumulators (5 x 64 TMEM
+//     columns) are live together and each of the nine 8 KB tap slices streams once per conv and stamp through a 6-stage ring.
+//     The price: a conv's epilogue cannot overlap its own MMAs (all tiles complete with the last tap).
+//
+// Warp roles (512 threads, one persistent CTA per SM): warp 0 producer (bulk copies: hi -> X, lo -> T, tap slices), warps 1-3 MMA
+// issue (tiles t = j mod 3; one thread sustains only ~1 tcgen05.mma per 57 cycles), warps 4-7 helpers (lo: T -> TMEM), warps 8-15
+// epilogue (two groups, alternate tiles).
+#include "conv_epilogue.cuh"
+#include "kernels.cuh"
+#include "launch.cuh"
+#include "umma_ptx.cuh"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace gd {
+
+constexpr int L2_C = 64;
+constexpr int L2_WP = 25;
+constexpr int L2_S = 625;                            // padded-linear rows of one stamp at 24x24
+constexpr int L2_PIX = 600;                          // rows of real image rows (y < 24)
+constexpr int L2_TILES = 5;
+constexpr int L2_GAP = 32;                           // >= Wp + 1
+constexpr int L2_PSTRIDE = L2_TILES * MTILE + L2_GAP;            // 672
+constexpr int L2_ACT_BYTES = (16 * L2_PSTRIDE + L2_GAP) * 16;    // 172,544: planes 0-7 = X, 8-15 = T
+constexpr int L2_WSTAGE = L2_C * L2_C * 2;           // 8,192: one tap of one conv, [8][64][8]
+constexpr int L2_WSTAGES = 6;
+constexpr int L2_SMEM = L2_ACT_BYTES + L2_WSTAGES * L2_WSTAGE;   // 221,696
+constexpr int L2_THREADS = (1 + 3 + 4 + 8) * 32;
+constexpr int L2_LO_COL = L2_TILES * L2_C;           // 320: packed lo stream, 32 columns per tile
+
+enum { L2B_X_FULL = 0, L2B_T_FULL, L2B_T_FREE, L2B_ACC_FULL, L2B_EPI_DONE, L2B_LO_DONE, L2B_W_FULL, L2B_W_EMPTY = L2B_W_FULL + L2_WSTAGES,
+       L2B_COUNT = L2B_W_EMPTY + L2_WSTAGES };
+
+struct L2ChainParams {
+    int nb, mode;                  // stamps; 0 = m_down2's ResBlocks (-> space-to-depth copy), 1 = m_up2's (+ U-Net skip -> fp16 map)
+    Geom g1, g2;                   // 24x24 and 12x12 geometry of the chunk
+    const void *x_hi, *x_lo;       // fp16 hi / lo planes of the stage's input stream [8][g1.Ptot][8]
+    const void* w[4];              // packed 3x3 weights [tap][8][64][8]
+    void* s2d;                     // mode 0: space-to-depth copy [32][g2.Ptot][8] for the strided conv
+    const float* skip32;           // mode 1: U-Net skip x2, fp32 [16][g1.Ptot][4]
+    void* out16;                   // mode 1: fp16 (x + x2) [8][g1.Ptot][8] (input of m_up1's transposed conv)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[L2B_COUNT];
+    __shared__ uint32_t tmem_slot;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    unsigned char* w_smem = smem + L2_ACT_BYTES;
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar(L2B_X_FULL), 1); mbar_init(bar(L2B_T_FULL), 1); mbar_init(bar(L2B_T_FREE), 3);
+        mbar_init(bar(L2B_ACC_FULL), 3); mbar_init(bar(L2B_EPI_DONE), 8); mbar_init(bar(L2B_LO_DONE), 4);
+        for (int s = 0; s < L2_WSTAGES; ++s) { mbar_init(bar(L2B_W_FULL + s), 1); mbar_init(bar(L2B_W_EMPTY + s), 3); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // zero the activation planes once: gap rows, the zero row below the stamp and the pad pixels are never written afterwards
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for (int i = threadIdx.x; i < L2_ACT_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int n_my = p.nb > (int)blockIdx.x ? (p.nb - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t Ptot1 = (uint32_t)p.g1.Ptot;
+    auto row_off = [](int pl, int s) { return (uint32_t)((pl * L2_PSTRIDE + L2_GAP + s) * 16); };
+
+    if (warp == 0) {
+        // ===== producer =====
+        if (lane == 0) {
+            uint32_t wc = 0;                              // running weight-stage counter
+            auto load_planes = [&](int b, const void* src, int pl0, uint32_t full) {
+                const size_t row0 = (size_t)p.g1.base0 + (size_t)b * p.g1.S;
+                mbar_expect_tx(full, 8u * L2_S * 16u);
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    bulk_g2s(smem_u32(smem) + row_off(pl0 + ch, 0), reinterpret_cast<const unsigned char*>(src) + ((size_t)ch * Ptot1 + row0) * 16,
+                             (uint32_t)L2_S * 16u, full);
+            };
+            for (int k = 0; k < n_my; ++k) {
+                const int b = (int)blockIdx.x + k * (int)gridDim.x;
+                // X: the previous item's last epilogue (conv 3, n = 4k - 1) has read its residual hi from it
+                mbar_wait(bar(L2B_EPI_DONE), (uint32_t)((4 * k - 1) & 1));
+                load_planes(b, p.x_hi, 0, bar(L2B_X_FULL));
+                mbar_wait(bar(L2B_T_FREE), (uint32_t)((k & 1) ^ 1));          // ... and its conv 3 has finished reading T
+                load_planes(b, p.x_lo, 8, bar(L2B_T_FULL));
+                for (int c = 0; c < 4; ++c)
+                    for (int tap = 0; tap < 9; ++tap, ++wc) {
+                        const uint32_t s = wc % L2_WSTAGES;
+                        mbar_wait(bar(L2B_W_EMPTY + s), ((wc / L2_WSTAGES) & 1) ^ 1);
+                        mbar_expect_tx(bar(L2B_W_FULL + s), (uint32_t)L2_WSTAGE);
+                        bulk_g2s(smem_u32(w_smem) + s * L2_WSTAGE, reinterpret_cast<const unsigned char*>(p.w[c]) + (size_t)tap * L2_WSTAGE, (uint32_t)L2_WSTAGE,
+                                 bar(L2B_W_FULL + s));
+                    }
+            }
+        }
+    } else if (warp <= 3) {
+        // ===== MMA issuers: warp 1 + jw owns tiles jw, jw + 3.  Tap-outer: all tiles of a conv accumulate together =====
+        const int jw = warp - 1;
+        const uint32_t idesc = instr_desc_f16(MTILE, L2_C);
+        const uint64_t a_desc0 = smem_desc(smem_u32(smem), L2_PSTRIDE * 16, 128);
+        const uint64_t w_desc0 = smem_desc(smem_u32(w_smem), L2_C * 16, 128);
+        constexpr uint32_t A_KK = 2 * L2_PSTRIDE, W_KK = 2 * L2_C;           // in 16-byte units
+        uint32_t wc = 0;
+        for (int k = 0; k < n_my; ++k) {
+            const uint32_t kp = (uint32_t)(k & 1);
+            mbar_wait(bar(L2B_X_FULL), kp);
+            for (int c = 0; c < 4; ++c) {
+                const int n = 4 * k + c;
+                // input complete: every epilogue of the previous conv (which also drained the accumulators) has arrived
+                mbar_wait(bar(L2B_EPI_DONE), (uint32_t)((n - 1) & 1));
+                tc_fence_after();
+                const int src_pl = (c & 1) ? 8 : 0;
+                for (int tap = 0; tap < 9; ++tap, ++wc) {
+                    const uint32_t s = wc % L2_WSTAGES;
+                    mbar_wait(bar(L2B_W_FULL + s), (wc / L2_WSTAGES) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int off = (tap / 3 - 1) * L2_WP + (tap % 3 - 1);
+                        const uint64_t wd = w_desc0 + (uint64_t)(s * (L2_WSTAGE >> 4));
+#pragma unroll
+                        for (int tt = 0; tt < 2; ++tt) {
+                            const int t = jw + 3 * tt;
+                            if (t < L2_TILES) {
+                                const uint32_t d = tmem + (uint32_t)(t * L2_C);
+                                const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(src_pl * L2_PSTRIDE + L2_GAP + t * MTILE + off);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    if (tap == 0 && kk == 0) tc_mma_f16(d, ad, wd, idesc, 0u);
+                                    else tc_mma_f16_acc(d, ad + (uint64_t)(kk * A_KK), wd + (uint64_t)(kk * W_KK), idesc);
+                                }
+                            }
+                        }
+                        tc_commit(bar(L2B_W_EMPTY + s));
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) {
+                    tc_commit(bar(L2B_ACC_FULL));
+                    if (c == 3) tc_commit(bar(L2B_T_FREE));
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 8) {
+        // ===== helpers: lo halves of the input stream, T -> TMEM (releases T for conv 0's output) =====
+        const int q = warp & 3;
+        for (int k = 0; k < n_my; ++k) {
+            mbar_wait(bar(L2B_T_FULL), (uint32_t)(k & 1));
+            mbar_wait(bar(L2B_EPI_DONE), (uint32_t)((4 * k - 1) & 1));       // the previous item's last epilogue has read the lo stream
+            tc_fence_after();
+            for (int t = 0; t < L2_TILES; ++t) {
+                const int s = t * MTILE + q * 32 + lane;
+                uint4 lo[8];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    lo[ch] = s < L2_S ? *reinterpret_cast<const uint4*>(smem + row_off(8 + ch, s)) : make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(L2_LO_COL + t * 32);
+                tc_st16(taddr, reinterpret_cast<const uint32_t*>(lo));
+                tc_st16(taddr + 16, reinterpret_cast<const uint32_t*>(lo) + 16);
+            }
+            tc_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(L2B_LO_DONE));
+        }
+    } else {
+        // ===== epilogue: group (warps 8-11 / 12-15) takes tiles t = grp, grp + 2, (grp + 4); 32-channel halves =====
+        const int q = warp & 3, grp = (warp - 8) >> 2;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        for (int k = 0; k < n_my; ++k) {
+            const int b = (int)blockIdx.x + k * (int)gridDim.x;
+            const uint32_t kp = (uint32_t)(k & 1);
+            for (int c = 0; c < 4; ++c) {
+                const int n = 4 * k + c;
+                mbar_wait(bar(L2B_ACC_FULL), (uint32_t)(n & 1));
+                if (c == 0) mbar_wait(bar(L2B_LO_DONE), kp);                 // T no longer holds the lo halves; the lo stream is in TMEM
+                tc_fence_after();
+                for (int t = grp; t < L2_TILES; t += 2) {
+                    const int s = t * MTILE + q * 32 + lane;
+                    const int y = (s * 2622) >> 16, x = s - y * L2_WP;       // s / 25 exactly for 0 <= s < 2000
+                    const bool valid = s < L2_PIX && x < 24;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const uint32_t acc_addr = tmem + lane_base + (uint32_t)(t * L2_C + hf * 32);
+                        const uint32_t lo_addr = tmem + lane_base + (uint32_t)(L2_LO_COL + t * 32 + hf * 16);
+                        uint32_t r0[16], r1[16], lo[16];
+                        tc_ld16_nowait(acc_addr, r0); tc_ld16_nowait(acc_addr + 16, r1);
+                        if (c & 1) tc_ld16_nowait(lo_addr, lo);
+                        uint4 hi[4];
+                        if (c & 1) {
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch) hi[ch] = *reinterpret_cast<const uint4*>(smem + row_off(4 * hf + ch, s));
+                        }
+                        tc_ld_wait16(r0); tc_ld_wait16(r1);
+                        if (c & 1) tc_ld_wait16(lo);
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r0[i]); v[16 + i] = __uint_as_float(r1[i]); }
+                        if (!(c & 1)) {
+                            if (valid) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+#pragma unroll
+                                for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(smem + row_off(8 + 4 * hf + ch, s)) = pack8_half(v + 8 * ch);
+                            }
+                        } else {
+                            const uint32_t* hi32 = reinterpret_cast<const uint32_t*>(hi);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float2 f = hilo_pair(hi32[i], lo[i]);
+                                v[2 * i] += f.x; v[2 * i + 1] += f.y;
+                            }
+                            if (c == 1) {
+                                uint4 nh[4], nl[4];
+#pragma unroll
+                                for (int ch = 0; ch < 4; ++ch) split8_hilo(v + 8 * ch, nh[ch], nl[ch]);
+                                tc_st16(lo_addr, reinterpret_cast<const uint32_t*>(nl));
+                                if (valid) {
+#pragma unroll
+                                    for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(smem + row_off(4 * hf + ch, s)) = nh[ch];
+                                }
+                            } else if (valid) {
+                                if (MODE == 0) {
+                                    // space-to-depth copy for m_down2's strided conv: K chunk = (dy*2+dx)*8 + channel chunk, coarse row of g2
+                                    const Geom& g2 = p.g2;
+                                    const int crow = g2.base0 + b * g2.S + (y >> 1) * g2.Wp + (x >> 1), ctap = ((y & 1) << 1) | (x & 1);
+                                    uint4* dst = reinterpret_cast<uint4*>(p.s2d) + (size_t)(ctap * 8 + 4 * hf) * g2.Ptot + crow;
+#pragma unroll
+                                    for (int ch = 0; ch < 4; ++ch) dst[(size_t)ch * g2.Ptot] = pack8_half(v + 8 * ch);
+                                } else {
+                                    const size_t row = (size_t)p.g1.base0 + (size_t)b * p.g1.S + (size_t)s;
+                                    const float4* sk = reinterpret_cast<const float4*>(p.skip32) + (size_t)(8 * hf) * Ptot1 + row;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float4 a = __ldg(sk + (size_t)i * Ptot1);
+                                        v[4 * i] += a.x; v[4 * i + 1] += a.y; v[4 * i + 2] += a.z; v[4 * i + 3] += a.w;
+                                    }
+                                    uint4* dst = reinterpret_cast<uint4*>(p.out16) + (size_t)(4 * hf) * Ptot1 + row;
+#pragma unroll
+                                    for (int ch = 0; ch < 4; ++ch) dst[(size_t)ch * Ptot1] = pack8_half(v + 8 * ch);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (c == 1) tc_st_wait();
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(L2B_EPI_DONE));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+static int g_l2_sms = 0;
+
+int conv_l2chain_init() {
+    int dev;
+    GD_CUDA_CHECK(cudaGetDevice(&dev));
+    GD_CUDA_CHECK(cudaDeviceGetAttribute(&g_l2_sms, cudaDevAttrMultiProcessorCount, dev));
+    GD_CUDA_CHECK(cudaFuncSetAttribute(k_l2_chain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
+    GD_CUDA_CHECK(cudaFuncSetAttribute(k_l2_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
+    return GD_OK;
+}
+
+int launch_l2chain(int mode, const Geom& g1, const Geom& g2, int nb, const void* x_hi, const void* x_lo, const void* const* w4, void* s2d,
+                   const float* skip32, void* out16, cudaStream_t st) {
+    if (nb <= 0) return GD_OK;
+    if (!g_l2_sms) { set_error("conv_l2chain: library not initialised"); return GD_ECUDA; }
+    if (g1.Wp != L2_WP || g1.S != L2_S || g2.Wp != 13) { set_error("conv_l2chain: needs the 24x24 / 12x12 geometries"); return GD_EUNSUPPORTED; }
+    L2ChainParams p;
+    memset(&p, 0, sizeof(p));
+    p.nb = nb; p.mode = mode; p.g1 = g1; p.g2 = g2; p.x_hi = x_hi; p.x_lo = x_lo; p.s2d = s2d; p.skip32 = skip32; p.out16 = out16;
+    for (int i = 0; i < 4; ++i) p.w[i] = w4[i];
+    if (!x_hi || !x_lo || !w4[0] || !w4[1] || !w4[2] || !w4[3] || (mode == 0 ? !s2d : (!skip32 || !out16))) {
+        set_error("conv_l2chain: missing buffer"); return GD_EBADSHAPE;
+    }
+    const int grid = nb < g_l2_sms ? nb : g_l2_sms;
+    cudaEvent_t e1 = nullptr;
+    const double flops = 4.0 * 2.0 * (double)nb * 576 * (double)L2_C * L2_C * 9;
+    { int rc = conv_profile_mark(flops, st, &e1); if (rc != GD_OK) return rc; }
+    if (mode == 0) k_l2_chain<0><<<grid, L2_THREADS, L2_SMEM, st>>>(p);
+    else k_l2_chain<1><<<grid, L2_THREADS, L2_SMEM, st>>>(p);
+    GD_LAUNCHED();
+    if (e1) GD_CUDA_CHECK(cudaEventRecord(e1, st));
+    return GD_OK;
+}
+
+}  // namespace gd

@@ -15,10 +15,13 @@ int conv_profile_mark(double flops, cudaStream_t st, cudaEvent_t* stop);
 int conv_rb_init();
 int conv_l1chain_init();
 int launch_l1chain_down(const Geom& g0, const Geom& g1, int nb, const float* t, const float* head_w_host, const void* const* w4, const void* wdown,
-                        float* skip32, void* x2_16, cudaStream_t st);
+                        float* skip32, void* x2_16, void* x2_lo, cudaStream_t st);
 size_t l1chain_scratch_bytes();
 int launch_l1chain_up(const Geom& g0, const Geom& g1, int nb, const void* x_in, const void* wup, const float* tail_w_host, const void* const* w4,
                       float* tail_part, void* scratch, cudaStream_t st);
+int conv_l2chain_init();
+int launch_l2chain(int mode, const Geom& g1, const Geom& g2, int nb, const void* x_hi, const void* x_lo, const void* const* w4, void* s2d,
+                   const float* skip32, void* out16, cudaStream_t st);
 bool conv_rb_supported(const ConvParams& p1, const ConvParams& p2);
 int launch_conv_rb(const ConvParams& p1, const ConvParams& p2, cudaStream_t st);
 
