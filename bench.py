@@ -11,7 +11,7 @@ their NCCL all-gather.  Weak scaling: every rank processes its own `stamps` gala
 
 Printed JSON (rank 0, one line): `value` = whole-job galaxies/s with inputs resident in HBM; `e2e` = the same call with
 pinned HOST inputs (H2D of obs/psf/alpha and D2H of the deconvolved stamps + ellipticities inside the timed region);
-`roofline` = the dominant kernel family (k_conv_umma and the level-0 chain kernel k_l1_chain, tcgen05 tap-GEMM) timed live per launch with CUDA events, algorithmic
+`roofline` = the dominant kernel family (k_conv_umma and the chain kernels k_l1_chain / k_l2_chain, tcgen05 tap-GEMM) timed live per launch with CUDA events, algorithmic
 FLOPs / time against the measured bf16 peak of MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle (bit-exact port of
 the reference's torch code) timed on this box's host cores on a bounded sample.
 
@@ -267,7 +267,7 @@ def main():
                 pass
             roof = dict(bound='tensor', achieved=ach, peak=P['tensor_sustained'], unit='TFLOP/s', frac=ach / P['tensor_sustained'], traffic=traffic,
                         traffic_note=traffic_note,
-                        kernel='k_conv_umma + k_l1_chain (tcgen05 tap-GEMM convolutions; k_l1_chain = 4 convs per launch)', launches_per_step=int(n_k.value), avg_launch_us=ms_k.value * 1e3 / max(1, n_k.value),
+                        kernel='k_conv_umma + k_l1_chain + k_l2_chain (tcgen05 tap-GEMM convolutions; the chain kernels run 4-5 convs per launch)', launches_per_step=int(n_k.value), avg_launch_us=ms_k.value * 1e3 / max(1, n_k.value),
                         kernel_share_of_step=ms_k.value / ms_profile_step, profiled_step_ms=ms_profile_step, flops_per_launch_avg=fl_k.value / max(1, n_k.value),
                         peak_source=P['source'] + ', sustained bf16 (kernel timed inside a long step); burst = %.1f' % P['tensor_burst'])
 

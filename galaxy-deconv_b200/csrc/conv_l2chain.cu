@@ -9,12 +9,20 @@
 //   * the residual stream is hi + lo: hi = the operand copy in X, lo = rn16(x - hi) packed two per column in TENSOR MEMORY
 //     (5 tiles x 32 columns) -- |x - (hi + lo)| <= 2^-22 |x| as in the HBM stream of the other levels;
 //   * a conv's weights (74 KB) do not fit beside X and T, so the MMA loop is TAP-OUTER: the five tiles' accumulators (5 x 64 TMEM
-//     columns) are live together and each of the nine 8 KB tap slices streams once per conv and stamp through a 6-stage ring.
-//     The price: a conv's epilogue cannot overlap its own MMAs (all tiles complete with the last tap).
+//     columns) are live together and each of the nine 8 KB tap slices streams ONCE per conv and stamp through a 7-stage ring;
+//   * to let a conv's epilogue overlap MMAs although every tile completes with the last tap, the tiles form two phases on the same
+//     ring: phase 0 (tiles 0, 1) runs L2_LAG taps ahead of phase 1 (tiles 2, 3, 4).  Phase 0's epilogue drains under the tail of
+//     phase 1, and the next conv's phase 0 starts as soon as the tiles it reads (0..2) are written back, while tiles 3 and 4 still
+//     drain.  Streaming the ring once per phase instead (no lag) starves the MMAs: 48 KB in flight cover < 1 us of phase-0 issue.
+//     Measured on one box (G(8), 10,000 stamps): no lag 57.3 k gal/s, lag 3 57.9 k, lag 4 58.1 k; without this kernel 55.4 k.
+//   * the N = 64 MMA reads 4 KB of A and 2 KB of B from shared memory: 48 cycles at 128 B/cycle against 32 cycles of math, so the
+//     tensor pipe cannot exceed 67 % here; the kernel runs at ~58 cycles per MMA while issuing (46 % over the launch,
+//     profiles/l2chain_stalls_r02.txt).
 //
-// Warp roles (512 threads, one persistent CTA per SM): warp 0 producer (bulk copies: hi -> X, lo -> T, tap slices), warps 1-3 MMA
-// issue (tiles t = j mod 3; one thread sustains only ~1 tcgen05.mma per 57 cycles), warps 4-7 helpers (lo: T -> TMEM), warps 8-15
-// epilogue (two groups, alternate tiles).
+// Warp roles (512 threads, one persistent CTA per SM): warp 0 producers (lane 0: tap slices; lane 1: hi -> X in two row ranges,
+// lo -> T, L2 prefetch of the next item), warps 1-3 MMA issue (one thread sustains only ~1 tcgen05.mma per 57 cycles), warps 4-15
+// epilogue in three groups of four quadrant warps (unit = tile x 32-channel half, round robin); warps 4-7 first move the lo halves
+// of the item's input stream from T to tensor memory.
 #include "conv_epilogue.cuh"
 #include "kernels.cuh"
 #include "launch.cuh"
@@ -34,13 +42,20 @@ constexpr int L2_GAP = 32;                           // >= Wp + 1
 constexpr int L2_PSTRIDE = L2_TILES * MTILE + L2_GAP;            // 672
 constexpr int L2_ACT_BYTES = (16 * L2_PSTRIDE + L2_GAP) * 16;    // 172,544: planes 0-7 = X, 8-15 = T
 constexpr int L2_WSTAGE = L2_C * L2_C * 2;           // 8,192: one tap of one conv, [8][64][8]
-constexpr int L2_WSTAGES = 6;
-constexpr int L2_SMEM = L2_ACT_BYTES + L2_WSTAGES * L2_WSTAGE;   // 221,696
+constexpr int L2_WSTAGES = 7;
+constexpr int L2_SMEM = L2_ACT_BYTES + L2_WSTAGES * L2_WSTAGE;   // 229,888
 constexpr int L2_THREADS = (1 + 3 + 4 + 8) * 32;
 constexpr int L2_LO_COL = L2_TILES * L2_C;           // 320: packed lo stream, 32 columns per tile
 
-enum { L2B_X_FULL = 0, L2B_T_FULL, L2B_T_FREE, L2B_ACC_FULL, L2B_EPI_DONE, L2B_LO_DONE, L2B_W_FULL, L2B_W_EMPTY = L2B_W_FULL + L2_WSTAGES,
-       L2B_COUNT = L2B_W_EMPTY + L2_WSTAGES };
+// tile phases of one conv: the MMAs of phase 1 run while the epilogue of phase 0 drains, and the next conv's phase 0 starts as soon
+// as the tiles it reads (0..2) have been written back
+constexpr int L2_PH0_TILES = 2;                      // phase 0 = tiles 0, 1; phase 1 = tiles 2, 3, 4
+constexpr int L2_EPI_GROUPS = 3;                     // warps 4-15: three groups of four quadrant warps
+constexpr int L2_LAG = 4;                            // phase 1 runs this many taps behind phase 0 on the same ring of tap slices
+constexpr int L2_X0_ROWS = (L2_PH0_TILES + 1) * MTILE;          // 384: rows of tiles 0..2, everything phase 0 reads
+
+enum { L2B_X_FULL = 0, L2B_T_FULL = 2, L2B_T_FREE, L2B_LO_DONE, L2B_ACC_FULL, L2B_TILE_DONE = L2B_ACC_FULL + 2, L2B_W_FULL = L2B_TILE_DONE + L2_TILES,
+       L2B_W_EMPTY = L2B_W_FULL + L2_WSTAGES, L2B_COUNT = L2B_W_EMPTY + L2_WSTAGES };
 
 struct L2ChainParams {
     int nb, mode;                  // stamps; 0 = m_down2's ResBlocks (-> space-to-depth copy), 1 = m_up2's (+ U-Net skip -> fp16 map)
@@ -63,8 +78,9 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
     if (threadIdx.x == 0) {
-        mbar_init(bar(L2B_X_FULL), 1); mbar_init(bar(L2B_T_FULL), 1); mbar_init(bar(L2B_T_FREE), 3);
-        mbar_init(bar(L2B_ACC_FULL), 3); mbar_init(bar(L2B_EPI_DONE), 8); mbar_init(bar(L2B_LO_DONE), 4);
+        mbar_init(bar(L2B_X_FULL), 1); mbar_init(bar(L2B_X_FULL + 1), 1); mbar_init(bar(L2B_T_FULL), 1); mbar_init(bar(L2B_T_FREE), 3); mbar_init(bar(L2B_LO_DONE), 4);
+        mbar_init(bar(L2B_ACC_FULL), 3); mbar_init(bar(L2B_ACC_FULL + 1), 3);
+        for (int t = 0; t < L2_TILES; ++t) mbar_init(bar(L2B_TILE_DONE + t), 8);          // 2 channel halves x 4 quadrant warps
         for (int s = 0; s < L2_WSTAGES; ++s) { mbar_init(bar(L2B_W_FULL + s), 1); mbar_init(bar(L2B_W_EMPTY + s), 3); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -84,191 +100,218 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
     const int n_my = p.nb > (int)blockIdx.x ? (p.nb - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const uint32_t Ptot1 = (uint32_t)p.g1.Ptot;
     auto row_off = [](int pl, int s) { return (uint32_t)((pl * L2_PSTRIDE + L2_GAP + s) * 16); };
+    // every tile's barrier completes once per conv: completion n = 4 * item + conv has parity n & 1
+    auto wait_tiles = [&](int t0, int t1, int n) {
+        for (int t = t0; t <= t1; ++t) mbar_wait(bar(L2B_TILE_DONE + t), (uint32_t)(n & 1));
+    };
 
     if (warp == 0) {
-        // ===== producer =====
+        // ===== producers: lane 0 streams the tap slices, lane 1 the activation planes (independent waits) =====
         if (lane == 0) {
             uint32_t wc = 0;                              // running weight-stage counter
-            auto load_planes = [&](int b, const void* src, int pl0, uint32_t full) {
-                const size_t row0 = (size_t)p.g1.base0 + (size_t)b * p.g1.S;
-                mbar_expect_tx(full, 8u * L2_S * 16u);
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch)
-                    bulk_g2s(smem_u32(smem) + row_off(pl0 + ch, 0), reinterpret_cast<const unsigned char*>(src) + ((size_t)ch * Ptot1 + row0) * 16,
-                             (uint32_t)L2_S * 16u, full);
-            };
-            for (int k = 0; k < n_my; ++k) {
-                const int b = (int)blockIdx.x + k * (int)gridDim.x;
-                // X: the previous item's last epilogue (conv 3, n = 4k - 1) has read its residual hi from it
-                mbar_wait(bar(L2B_EPI_DONE), (uint32_t)((4 * k - 1) & 1));
-                load_planes(b, p.x_hi, 0, bar(L2B_X_FULL));
-                mbar_wait(bar(L2B_T_FREE), (uint32_t)((k & 1) ^ 1));          // ... and its conv 3 has finished reading T
-                load_planes(b, p.x_lo, 8, bar(L2B_T_FULL));
+            for (int k = 0; k < n_my; ++k)
                 for (int c = 0; c < 4; ++c)
                     for (int tap = 0; tap < 9; ++tap, ++wc) {
                         const uint32_t s = wc % L2_WSTAGES;
                         mbar_wait(bar(L2B_W_EMPTY + s), ((wc / L2_WSTAGES) & 1) ^ 1);
                         mbar_expect_tx(bar(L2B_W_FULL + s), (uint32_t)L2_WSTAGE);
-                        bulk_g2s(smem_u32(w_smem) + s * L2_WSTAGE, reinterpret_cast<const unsigned char*>(p.w[c]) + (size_t)tap * L2_WSTAGE, (uint32_t)L2_WSTAGE,
-                                 bar(L2B_W_FULL + s));
+                        bulk_g2s(smem_u32(w_smem) + s * L2_WSTAGE, reinterpret_cast<const unsigned char*>(p.w[c]) + (size_t)tap * L2_WSTAGE,
+                                 (uint32_t)L2_WSTAGE, bar(L2B_W_FULL + s));
                     }
+        } else if (lane == 1) {
+            auto plane_src = [&](const void* src, int ch, int b) {
+                return reinterpret_cast<const unsigned char*>(src) + ((size_t)ch * Ptot1 + (size_t)p.g1.base0 + (size_t)b * p.g1.S) * 16;
+            };
+            auto load_planes = [&](int b, const void* src, int pl0, int r0, int r1, uint32_t full) {
+                mbar_expect_tx(full, 8u * (uint32_t)(r1 - r0) * 16u);
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    bulk_g2s(smem_u32(smem) + row_off(pl0 + ch, r0), plane_src(src, ch, b) + (size_t)r0 * 16, (uint32_t)(r1 - r0) * 16u, full);
+            };
+            for (int k = 0; k < n_my; ++k) {
+                const int b = (int)blockIdx.x + k * (int)gridDim.x;
+                mbar_wait(bar(L2B_T_FREE), (uint32_t)((k & 1) ^ 1));          // the previous item's conv 3 has finished reading T
+                load_planes(b, p.x_lo, 8, 0, L2_S, bar(L2B_T_FULL));
+                // X in two parts, each as soon as the previous item's last epilogues (n = 4k - 1) have read their residual hi from it
+                wait_tiles(0, L2_PH0_TILES, 4 * k - 1);
+                load_planes(b, p.x_hi, 0, 0, L2_X0_ROWS, bar(L2B_X_FULL));
+                wait_tiles(L2_PH0_TILES + 1, L2_TILES - 1, 4 * k - 1);
+                load_planes(b, p.x_hi, 0, L2_X0_ROWS, L2_S, bar(L2B_X_FULL + 1));
+                if (k + 1 < n_my) {                       // the next item's planes (and this item's skip) on their way into L2
+                    const int bn = b + (int)gridDim.x;
+                    for (int ch = 0; ch < 8; ++ch) { bulk_prefetch_l2(plane_src(p.x_hi, ch, bn), L2_S * 16u); bulk_prefetch_l2(plane_src(p.x_lo, ch, bn), L2_S * 16u); }
+                }
+                if (MODE == 1)
+                    for (int ch = 0; ch < 16; ++ch) bulk_prefetch_l2(plane_src(p.skip32, ch, b), L2_S * 16u);
             }
         }
     } else if (warp <= 3) {
-        // ===== MMA issuers: warp 1 + jw owns tiles jw, jw + 3.  Tap-outer: all tiles of a conv accumulate together =====
+        // ===== MMA issuers.  Tap-outer within a phase: phase 0 = tiles 0, 1 (warps 1, 2), phase 1 = tiles 2, 3, 4 (warps 3, 1, 2) =====
         const int jw = warp - 1;
         const uint32_t idesc = instr_desc_f16(MTILE, L2_C);
         const uint64_t a_desc0 = smem_desc(smem_u32(smem), L2_PSTRIDE * 16, 128);
         const uint64_t w_desc0 = smem_desc(smem_u32(w_smem), L2_C * 16, 128);
         constexpr uint32_t A_KK = 2 * L2_PSTRIDE, W_KK = 2 * L2_C;           // in 16-byte units
-        uint32_t wc = 0;
+        uint32_t wc0 = 0;                                 // ring position of the conv's tap 0
+        const int t0 = jw, t1 = L2_PH0_TILES + (jw + 1) % 3;                 // this warp's tile of phase 0 (jw < 2 only) and of phase 1
         for (int k = 0; k < n_my; ++k) {
-            const uint32_t kp = (uint32_t)(k & 1);
-            mbar_wait(bar(L2B_X_FULL), kp);
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 4; ++c, wc0 += 9) {
                 const int n = 4 * k + c;
-                // input complete: every epilogue of the previous conv (which also drained the accumulators) has arrived
-                mbar_wait(bar(L2B_EPI_DONE), (uint32_t)((n - 1) & 1));
-                tc_fence_after();
                 const int src_pl = (c & 1) ? 8 : 0;
-                for (int tap = 0; tap < 9; ++tap, ++wc) {
-                    const uint32_t s = wc % L2_WSTAGES;
-                    mbar_wait(bar(L2B_W_FULL + s), (wc / L2_WSTAGES) & 1);
-                    tc_fence_after();
+                auto issue = [&](int t, int tap, uint32_t s) {
+                    const int off = (tap / 3 - 1) * L2_WP + (tap % 3 - 1);
+                    const uint64_t wd = w_desc0 + (uint64_t)(s * (L2_WSTAGE >> 4));
+                    const uint32_t d = tmem + (uint32_t)(t * L2_C);
+                    const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(src_pl * L2_PSTRIDE + L2_GAP + t * MTILE + off);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        if (tap == 0 && kk == 0) tc_mma_f16(d, ad, wd, idesc, 0u);
+                        else tc_mma_f16_acc(d, ad + (uint64_t)(kk * A_KK), wd + (uint64_t)(kk * W_KK), idesc);
+                    }
+                };
+                // input rows written back (tile t reads the rows of tiles t-1 .. t+1) and accumulators drained: tiles 0..2 for phase 0
+                wait_tiles(0, L2_PH0_TILES, n - 1);
+                if (c == 0) mbar_wait(bar(L2B_X_FULL), (uint32_t)(k & 1));
+                tc_fence_after();
+                constexpr int LAG = L2_LAG;
+                for (int i = 0; i < 9 + LAG; ++i) {
+                    if (i == LAG) {                    // ... tiles 3, 4 for phase 1
+                        wait_tiles(L2_PH0_TILES + 1, L2_TILES - 1, n - 1);
+                        if (c == 0) mbar_wait(bar(L2B_X_FULL + 1), (uint32_t)(k & 1));
+                        tc_fence_after();
+                    }
+                    if (i < 9) {
+                        const uint32_t w = wc0 + (uint32_t)i;
+                        mbar_wait(bar(L2B_W_FULL + w % L2_WSTAGES), (w / L2_WSTAGES) & 1);
+                        tc_fence_after();
+                    }
                     if (elect_one()) {
-                        const int off = (tap / 3 - 1) * L2_WP + (tap % 3 - 1);
-                        const uint64_t wd = w_desc0 + (uint64_t)(s * (L2_WSTAGE >> 4));
-#pragma unroll
-                        for (int tt = 0; tt < 2; ++tt) {
-                            const int t = jw + 3 * tt;
-                            if (t < L2_TILES) {
-                                const uint32_t d = tmem + (uint32_t)(t * L2_C);
-                                const uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(src_pl * L2_PSTRIDE + L2_GAP + t * MTILE + off);
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) {
-                                    if (tap == 0 && kk == 0) tc_mma_f16(d, ad, wd, idesc, 0u);
-                                    else tc_mma_f16_acc(d, ad + (uint64_t)(kk * A_KK), wd + (uint64_t)(kk * W_KK), idesc);
-                                }
-                            }
+                        if (i < 9 && jw < L2_PH0_TILES) issue(t0, i, (wc0 + (uint32_t)i) % L2_WSTAGES);
+                        if (i == 8) tc_commit(bar(L2B_ACC_FULL));
+                        if (i >= LAG) {
+                            const uint32_t s = (wc0 + (uint32_t)(i - LAG)) % L2_WSTAGES;
+                            issue(t1, i - LAG, s);
+                            tc_commit(bar(L2B_W_EMPTY + s));
                         }
-                        tc_commit(bar(L2B_W_EMPTY + s));
                     }
                     __syncwarp();
                 }
                 if (elect_one()) {
-                    tc_commit(bar(L2B_ACC_FULL));
+                    tc_commit(bar(L2B_ACC_FULL + 1));
                     if (c == 3) tc_commit(bar(L2B_T_FREE));
                 }
                 __syncwarp();
             }
         }
-    } else if (warp < 8) {
-        // ===== helpers: lo halves of the input stream, T -> TMEM (releases T for conv 0's output) =====
-        const int q = warp & 3;
-        for (int k = 0; k < n_my; ++k) {
-            mbar_wait(bar(L2B_T_FULL), (uint32_t)(k & 1));
-            mbar_wait(bar(L2B_EPI_DONE), (uint32_t)((4 * k - 1) & 1));       // the previous item's last epilogue has read the lo stream
-            tc_fence_after();
-            for (int t = 0; t < L2_TILES; ++t) {
-                const int s = t * MTILE + q * 32 + lane;
-                uint4 lo[8];
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch)
-                    lo[ch] = s < L2_S ? *reinterpret_cast<const uint4*>(smem + row_off(8 + ch, s)) : make_uint4(0u, 0u, 0u, 0u);
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(L2_LO_COL + t * 32);
-                tc_st16(taddr, reinterpret_cast<const uint32_t*>(lo));
-                tc_st16(taddr + 16, reinterpret_cast<const uint32_t*>(lo) + 16);
-            }
-            tc_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(L2B_LO_DONE));
-        }
     } else {
-        // ===== epilogue: group (warps 8-11 / 12-15) takes tiles t = grp, grp + 2, (grp + 4); 32-channel halves =====
-        const int q = warp & 3, grp = (warp - 8) >> 2;
+        // ===== epilogue: warps 4-15 = three groups of four quadrant warps; unit u = (tile u >> 1, channel half u & 1) goes to group
+        // u mod 3.  Warps 4-7 (the group with three units) first move the lo halves of the item's input stream T -> tensor memory =====
+        const int q = warp & 3, grp = (L2_EPI_GROUPS - 1) - ((warp - 4) >> 2);
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         for (int k = 0; k < n_my; ++k) {
             const int b = (int)blockIdx.x + k * (int)gridDim.x;
-            const uint32_t kp = (uint32_t)(k & 1);
+            if (warp < 8) {
+                mbar_wait(bar(L2B_T_FULL), (uint32_t)(k & 1));
+                wait_tiles(0, L2_TILES - 1, 4 * k - 1);                      // the previous item's last epilogues have read the lo stream
+                tc_fence_after();
+                for (int t = 0; t < L2_TILES; ++t) {
+                    const int s = t * MTILE + q * 32 + lane;
+                    uint4 lo[8];
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch)
+                        lo[ch] = s < L2_S ? *reinterpret_cast<const uint4*>(smem + row_off(8 + ch, s)) : make_uint4(0u, 0u, 0u, 0u);
+                    const uint32_t taddr = tmem + lane_base + (uint32_t)(L2_LO_COL + t * 32);
+                    tc_st16(taddr, reinterpret_cast<const uint32_t*>(lo));
+                    tc_st16(taddr + 16, reinterpret_cast<const uint32_t*>(lo) + 16);
+                }
+                tc_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(L2B_LO_DONE));
+            }
             for (int c = 0; c < 4; ++c) {
                 const int n = 4 * k + c;
-                mbar_wait(bar(L2B_ACC_FULL), (uint32_t)(n & 1));
-                if (c == 0) mbar_wait(bar(L2B_LO_DONE), kp);                 // T no longer holds the lo halves; the lo stream is in TMEM
-                tc_fence_after();
-                for (int t = grp; t < L2_TILES; t += 2) {
+                int ph_waited = -1;
+                for (int u = grp; u < 2 * L2_TILES; u += L2_EPI_GROUPS) {
+                    const int t = u >> 1, hf = u & 1, ph = t < L2_PH0_TILES ? 0 : 1;
+                    if (ph != ph_waited) {
+                        if (ph_waited < 0 && ph == 1) mbar_wait(bar(L2B_ACC_FULL), (uint32_t)(n & 1));     // keep every barrier at most one phase ahead
+                        mbar_wait(bar(L2B_ACC_FULL + ph), (uint32_t)(n & 1));
+                        if (c == 0 && ph_waited < 0) mbar_wait(bar(L2B_LO_DONE), (uint32_t)(k & 1));   // T no longer holds the lo halves
+                        tc_fence_after();
+                        ph_waited = ph;
+                    }
                     const int s = t * MTILE + q * 32 + lane;
                     const int y = (s * 2622) >> 16, x = s - y * L2_WP;       // s / 25 exactly for 0 <= s < 2000
                     const bool valid = s < L2_PIX && x < 24;
+                    const uint32_t acc_addr = tmem + lane_base + (uint32_t)(t * L2_C + hf * 32);
+                    const uint32_t lo_addr = tmem + lane_base + (uint32_t)(L2_LO_COL + t * 32 + hf * 16);
+                    uint32_t r0[16], r1[16], lo[16];
+                    tc_ld16_nowait(acc_addr, r0); tc_ld16_nowait(acc_addr + 16, r1);
+                    if (c & 1) tc_ld16_nowait(lo_addr, lo);
+                    uint4 hi[4];
+                    if (c & 1) {
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const uint32_t acc_addr = tmem + lane_base + (uint32_t)(t * L2_C + hf * 32);
-                        const uint32_t lo_addr = tmem + lane_base + (uint32_t)(L2_LO_COL + t * 32 + hf * 16);
-                        uint32_t r0[16], r1[16], lo[16];
-                        tc_ld16_nowait(acc_addr, r0); tc_ld16_nowait(acc_addr + 16, r1);
-                        if (c & 1) tc_ld16_nowait(lo_addr, lo);
-                        uint4 hi[4];
-                        if (c & 1) {
+                        for (int ch = 0; ch < 4; ++ch) hi[ch] = *reinterpret_cast<const uint4*>(smem + row_off(4 * hf + ch, s));
+                    }
+                    tc_ld_wait16(r0); tc_ld_wait16(r1);
+                    if (c & 1) tc_ld_wait16(lo);
+                    float v[32];
 #pragma unroll
-                            for (int ch = 0; ch < 4; ++ch) hi[ch] = *reinterpret_cast<const uint4*>(smem + row_off(4 * hf + ch, s));
+                    for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r0[i]); v[16 + i] = __uint_as_float(r1[i]); }
+                    if (!(c & 1)) {
+                        if (valid) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(smem + row_off(8 + 4 * hf + ch, s)) = pack8_half(v + 8 * ch);
                         }
-                        tc_ld_wait16(r0); tc_ld_wait16(r1);
-                        if (c & 1) tc_ld_wait16(lo);
-                        float v[32];
+                    } else {
+                        const uint32_t* hi32 = reinterpret_cast<const uint32_t*>(hi);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r0[i]); v[16 + i] = __uint_as_float(r1[i]); }
-                        if (!(c & 1)) {
+                        for (int i = 0; i < 16; ++i) {
+                            const float2 f = hilo_pair(hi32[i], lo[i]);
+                            v[2 * i] += f.x; v[2 * i + 1] += f.y;
+                        }
+                        if (c == 1) {
+                            uint4 nh[4], nl[4];
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch) split8_hilo(v + 8 * ch, nh[ch], nl[ch]);
+                            tc_st16(lo_addr, reinterpret_cast<const uint32_t*>(nl));
                             if (valid) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-#pragma unroll
-                                for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(smem + row_off(8 + 4 * hf + ch, s)) = pack8_half(v + 8 * ch);
+                                for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(smem + row_off(4 * hf + ch, s)) = nh[ch];
                             }
-                        } else {
-                            const uint32_t* hi32 = reinterpret_cast<const uint32_t*>(hi);
+                            tc_st_wait();
+                        } else if (valid) {
+                            if (MODE == 0) {
+                                // space-to-depth copy for m_down2's strided conv: K chunk = (dy*2+dx)*8 + channel chunk, coarse row of g2
+                                const Geom& g2 = p.g2;
+                                const int crow = g2.base0 + b * g2.S + (y >> 1) * g2.Wp + (x >> 1), ctap = ((y & 1) << 1) | (x & 1);
+                                uint4* dst = reinterpret_cast<uint4*>(p.s2d) + (size_t)(ctap * 8 + 4 * hf) * g2.Ptot + crow;
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float2 f = hilo_pair(hi32[i], lo[i]);
-                                v[2 * i] += f.x; v[2 * i + 1] += f.y;
-                            }
-                            if (c == 1) {
-                                uint4 nh[4], nl[4];
+                                for (int ch = 0; ch < 4; ++ch) dst[(size_t)ch * g2.Ptot] = pack8_half(v + 8 * ch);
+                            } else {
+                                const size_t row = (size_t)p.g1.base0 + (size_t)b * p.g1.S + (size_t)s;
+                                const float4* sk = reinterpret_cast<const float4*>(p.skip32) + (size_t)(8 * hf) * Ptot1 + row;
 #pragma unroll
-                                for (int ch = 0; ch < 4; ++ch) split8_hilo(v + 8 * ch, nh[ch], nl[ch]);
-                                tc_st16(lo_addr, reinterpret_cast<const uint32_t*>(nl));
-                                if (valid) {
-#pragma unroll
-                                    for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(smem + row_off(4 * hf + ch, s)) = nh[ch];
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 a = __ldg(sk + (size_t)i * Ptot1);
+                                    v[4 * i] += a.x; v[4 * i + 1] += a.y; v[4 * i + 2] += a.z; v[4 * i + 3] += a.w;
                                 }
-                            } else if (valid) {
-                                if (MODE == 0) {
-                                    // space-to-depth copy for m_down2's strided conv: K chunk = (dy*2+dx)*8 + channel chunk, coarse row of g2
-                                    const Geom& g2 = p.g2;
-                                    const int crow = g2.base0 + b * g2.S + (y >> 1) * g2.Wp + (x >> 1), ctap = ((y & 1) << 1) | (x & 1);
-                                    uint4* dst = reinterpret_cast<uint4*>(p.s2d) + (size_t)(ctap * 8 + 4 * hf) * g2.Ptot + crow;
+                                uint4* dst = reinterpret_cast<uint4*>(p.out16) + (size_t)(4 * hf) * Ptot1 + row;
 #pragma unroll
-                                    for (int ch = 0; ch < 4; ++ch) dst[(size_t)ch * g2.Ptot] = pack8_half(v + 8 * ch);
-                                } else {
-                                    const size_t row = (size_t)p.g1.base0 + (size_t)b * p.g1.S + (size_t)s;
-                                    const float4* sk = reinterpret_cast<const float4*>(p.skip32) + (size_t)(8 * hf) * Ptot1 + row;
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        const float4 a = __ldg(sk + (size_t)i * Ptot1);
-                                        v[4 * i] += a.x; v[4 * i + 1] += a.y; v[4 * i + 2] += a.z; v[4 * i + 3] += a.w;
-                                    }
-                                    uint4* dst = reinterpret_cast<uint4*>(p.out16) + (size_t)(4 * hf) * Ptot1 + row;
-#pragma unroll
-                                    for (int ch = 0; ch < 4; ++ch) dst[(size_t)ch * Ptot1] = pack8_half(v + 8 * ch);
-                                }
+                                for (int ch = 0; ch < 4; ++ch) dst[(size_t)ch * Ptot1] = pack8_half(v + 8 * ch);
                             }
                         }
                     }
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(L2B_TILE_DONE + t));
                 }
-                if (c == 1) tc_st_wait();
-                tc_fence_before();
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(L2B_EPI_DONE));
+                // a group whose units all lie in phase 0 or all in phase 1 still has to follow both accumulator barriers
+                if (ph_waited == 0) mbar_wait(bar(L2B_ACC_FULL + 1), (uint32_t)(n & 1));
             }
         }
     }

@@ -45,6 +45,7 @@ print(json.dumps({'golden': err_golden, 'big': err_big, 'finite': bool(torch.isf
 VARIANTS = [
     {},
     {'GDECONV_L1CHAIN': '0'},
+    {'GDECONV_L2CHAIN': '0'},
     {'GDECONV_FUSE_RB': '0'},
     {'GDECONV_FUSE_RB': '2'},
     {'GDECONV_HILO': '0'},
