@@ -322,7 +322,8 @@ extern "C" int gd_pack_weights(int arch, int n_iters, const GdTensorDesc* tensor
         slot((const void**)&W.rho_param, pack_f32(bl, r.data(), r.size()));
         W.has_rho_param = 1;
     }
-    if (!W.has_resunet && !W.has_subnet) GD_FAIL(GD_EBADSHAPE, "state_dict holds neither ResUNet (m_head.weight) nor SubNet (init.mlp.0.weight) tensors");
+    if (!W.has_resunet && !W.has_subnet && !W.has_rho_param)
+        GD_FAIL(GD_EBADSHAPE, "state_dict holds neither ResUNet (m_head.weight) nor SubNet (init.mlp.0.weight) nor rho parameter tensors");
 
     W.blob_bytes = align_up(bl.host.size(), 256);
     bl.host.resize(W.blob_bytes, 0);
@@ -741,6 +742,32 @@ extern "C" int gd_subnet_forward(const GdWeights* W, const float* psf, const flo
     return launch_subnet(W->sub, psf, alpha, rho_out, batch, (cudaStream_t)stream);
 }
 
+// Path U on one chunk (models/Unrolled_ADMM.py:177-215, :396-442; models/ADMMNet.py:97-129) with the Z-update supplied by the caller:
+// `zupdate` maps the denoiser input ws.t (scaled by ws.tscale when `scaled`) to ws.z.  `analysis` points at this chunk's first stamp.
+template <class ZUpdate>
+static int admm_u_chunk(const GdWeights* W, const Ws& ws, int llh, int flags, const float* yc, const float* kc, const float* ac, float* outc,
+                        float* analysis, size_t plane, int nb, cudaStream_t st, bool scaled, ZUpdate zupdate) {
+    const int n = W->n_iters, nr = W->n_rho;
+    const size_t ni = (size_t)nb * NPIX;
+    float* u1 = ws.u;
+    GD_TRY(launch_u_prologue(yc, kc, ac, flags & 1, ws.spec, ws.x, ws.z, ws.v, u1, ws.u2, ws.Hx, nb, st));
+    auto dump = [&](int slot) -> int {
+        if (!analysis) return GD_OK;
+        float* A = analysis + (size_t)slot * 5 * plane;
+        const float* src[5] = {ws.v, ws.z, ws.x, u1, ws.u2};
+        for (int q = 0; q < 5; ++q) GD_TRY(copy_f32(A + q * plane, src[q], ni, st));
+        return GD_OK;
+    };
+    GD_TRY(dump(0));
+    for (int it = 0; it < n; ++it) {
+        GD_TRY(launch_u_pre(llh, yc, ac, ws.rho, nr, n, it, ws.x, u1, ws.u2, ws.Hx, ws.v, ws.t, scaled ? ws.tscale : nullptr, nb, st));
+        GD_TRY(zupdate());
+        GD_TRY(launch_u_post(ws.spec, ws.rho, nr, n, it, ws.z, ws.v, ws.x, u1, ws.u2, ws.Hx, nb, st));
+        GD_TRY(dump(it + 1));
+    }
+    return launch_scale_by_alpha(outc, ws.x, ac, nb, llh == GD_LLH_POISSON || (flags & 2), st);     // Unrolled_ADMM.py:215 / ADMMNet.py:129
+}
+
 extern "C" int gd_admm_forward(const GdWeights* W, int llh, int u_v0_over_alpha, const float* y, const float* psf,
                                const float* alpha, float* out, float* rho_out, float* analysis, int batch,
                                void* workspace, size_t workspace_bytes, void* stream) {
@@ -776,24 +803,36 @@ extern "C" int gd_admm_forward(const GdWeights* W, int llh, int u_v0_over_alpha,
                 }
             }
         } else {
-            float* u1 = ws.u;
-            GD_TRY(launch_u_prologue(yc, kc, ac, u_v0_over_alpha & 1, ws.spec, ws.x, ws.z, ws.v, u1, ws.u2, ws.Hx, nb, st));
-            auto dump = [&](int slot) -> int {
-                if (!analysis) return GD_OK;
-                float* A = analysis + (size_t)slot * 5 * plane + o;
-                const float* src[5] = {ws.v, ws.z, ws.x, u1, ws.u2};
-                for (int q = 0; q < 5; ++q) GD_TRY(copy_f32(A + q * plane, src[q], ni, st));
-                return GD_OK;
-            };
-            GD_TRY(dump(0));
-            for (int it = 0; it < n; ++it) {
-                GD_TRY(launch_u_pre(llh, yc, ac, ws.rho, nr, n, it, ws.x, u1, ws.u2, ws.Hx, ws.v, ws.t, ws.tscale, nb, st));
-                GD_TRY(resunet_chunk(W, ws, ws.t, ws.tscale, ws.z, nb, st));
-                GD_TRY(launch_u_post(ws.spec, ws.rho, nr, n, it, ws.z, ws.v, ws.x, u1, ws.u2, ws.Hx, nb, st));
-                GD_TRY(dump(it + 1));
-            }
-            GD_TRY(launch_scale_by_alpha(out + o, ws.x, ac, nb, llh == GD_LLH_POISSON || (u_v0_over_alpha & 2), st));     // Unrolled_ADMM.py:215 / ADMMNet.py:129     // Unrolled_ADMM.py:215
+            GD_TRY(admm_u_chunk(W, ws, llh, u_v0_over_alpha, yc, kc, ac, out + o, analysis ? analysis + o : nullptr, plane, nb, st, true,
+                                [&]() { return resunet_chunk(W, ws, ws.t, ws.tscale, ws.z, nb, st); }));
         }
+    }
+    return GD_OK;
+}
+
+// Unrolled_ADMM / ADMMNet with denoiser='XDenseUNet' (models/Unrolled_ADMM.py:142-151,163; models/ADMMNet.py:65-74,87): the path-U loop of
+// gd_admm_forward with the Z-update z = XDenseUNet(x + u1) run by csrc/xdense.cu in fp32 on the UNSCALED input.  `W` carries the SubNet or
+// the rho parameters only (packed from the same state_dict; it need not hold a ResUNet), `X` the packed XDenseUNet.
+extern "C" int gd_admm_forward_xdense(const GdWeights* W, const GdXDense* X, int llh, int flags, const float* y, const float* psf,
+                                      const float* alpha, float* out, float* rho_out, float* analysis, int batch, void* workspace,
+                                      size_t workspace_bytes, void* xd_workspace, size_t xd_workspace_bytes, int xd_chunk, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!W || !X) GD_FAIL(GD_EBADSHAPE, "gd_admm_forward_xdense: NULL weights");
+    if (W->arch != GD_ARCH_U) GD_FAIL(GD_EUNSUPPORTED, "the XDenseUNet denoiser exists for Unrolled_ADMM / ADMMNet (arch U) only");
+    if (batch < 0 || (batch && (!y || !psf || !alpha || !out))) GD_FAIL(GD_EBADSHAPE, "gd_admm_forward_xdense: bad batch or NULL buffers");
+    if (llh != GD_LLH_GAUSSIAN && llh != GD_LLH_POISSON) GD_FAIL(GD_EUNSUPPORTED, "unknown likelihood %d", llh);
+    GD_CUDA_CHECK(cudaSetDevice(W->device));
+    Ws ws; int chunk;
+    GD_TRY(ws_check(workspace, workspace_bytes, W, &ws, &chunk));
+    const int nr = W->n_rho;
+    const size_t plane = (size_t)batch * NPIX;
+    for (int c0 = 0; c0 < batch; c0 += chunk) {
+        const int nb = batch - c0 < chunk ? batch - c0 : chunk;
+        const size_t o = (size_t)c0 * NPIX;
+        GD_TRY(rho_chunk(W, ws, psf + o, alpha + c0, nb, st));
+        if (rho_out) GD_TRY(copy_f32(rho_out + (size_t)c0 * nr, ws.rho, (size_t)nb * nr, st));
+        GD_TRY(admm_u_chunk(W, ws, llh, flags, y + o, psf + o, alpha + c0, out + o, analysis ? analysis + o : nullptr, plane, nb, st, false,
+                            [&]() { return gd_xdense_forward(X, ws.t, ws.z, nb, xd_workspace, xd_workspace_bytes, xd_chunk, stream); }));
     }
     return GD_OK;
 }

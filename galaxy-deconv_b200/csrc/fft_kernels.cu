@@ -514,10 +514,12 @@ __global__ void __launch_bounds__(G_THREADS) k_u_pre(int llh, const float* __res
         tv[e] = x[i] + u1[i];
         amax = fmaxf(amax, fabsf(tv[e]));
     }
-    amax = block_max(amax, red);
-    float inv;
-    float s = pow2_scale(amax, &inv);
-    if (threadIdx.x == 0) tscale[b] = s;
+    float inv = 1.f;
+    if (tscale) {          // tscale == nullptr: unscaled denoiser input (XDenseUNet has BatchNorm shifts and biases: not homogeneous)
+        amax = block_max(amax, red);
+        float s = pow2_scale(amax, &inv);
+        if (threadIdx.x == 0) tscale[b] = s;
+    }
 #pragma unroll
     for (int e = 0; e < NPIX / G_THREADS; ++e) t[o + threadIdx.x + e * G_THREADS] = tv[e] * inv;
 }

@@ -20,7 +20,7 @@ PRECISIONS = {'fp32_simt': PREC_FP32_SIMT, 'fp16_umma': PREC_FP16_UMMA, 'fp16_si
 SYMBOLS = ('gd_version', 'gd_last_error', 'gd_pack_weights', 'gd_free_weights', 'gd_workspace_bytes', 'gd_workspace_init',
            'gd_admm_forward', 'gd_resunet_forward', 'gd_subnet_forward', 'gd_fft_solver', 'gd_conv_fft', 'gd_moments_e',
            'gd_launch_count', 'gd_debug_geom', 'gd_debug_tapgemm', 'gd_profile_begin', 'gd_profile_end', 'gd_pack_xdense', 'gd_free_xdense', 'gd_xdense_workspace_bytes',
-           'gd_xdense_forward', 'gd_tikhonet_forward', 'gd_psf_to_otf', 'gd_conv_otf', 'gd_max_chunk', 'gd_debug_divmagic')
+           'gd_xdense_forward', 'gd_tikhonet_forward', 'gd_admm_forward_xdense', 'gd_psf_to_otf', 'gd_conv_otf', 'gd_max_chunk', 'gd_debug_divmagic')
 
 
 class GdTensorDesc(C.Structure):
@@ -62,6 +62,7 @@ def _load():
     lib.gd_xdense_workspace_bytes.restype = sz
     lib.gd_xdense_forward.argtypes = [vp, vp, vp, i, vp, sz, i, vp]
     lib.gd_tikhonet_forward.argtypes = [vp, i, f, vp, vp, vp, vp, i, vp, sz, i, vp]
+    lib.gd_admm_forward_xdense.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, i, vp, sz, vp, sz, i, vp]
     lib.gd_psf_to_otf.argtypes = [vp, i, i, i, vp, vp, i, vp]
     lib.gd_conv_otf.argtypes = [vp, i, vp, vp, i, vp]
     lib.gd_max_chunk.restype = i

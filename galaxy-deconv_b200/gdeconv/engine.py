@@ -279,7 +279,8 @@ class AdmmEngine:
         return g['out'].clone()
 
     def admm(self, y, psf, alpha, llh=_lib.LLH_GAUSSIAN, v0_over_alpha=False, want_rho=False, want_analysis=False,
-             precision=None, times_alpha=False):
+             precision=None, times_alpha=False, xdense=None):
+        """xdense: an XDenseEngine -> the Z-update is that XDenseUNet (gd_admm_forward_xdense, arch U only) instead of the ResUNet."""
         v0_over_alpha = int(bool(v0_over_alpha)) | (2 if times_alpha else 0)          # flag word of gd_admm_forward
         y = require_cuda_stamps('y', y)
         B, dev = y.shape[0], y.device
@@ -297,6 +298,13 @@ class AdmmEngine:
                 shape = (self.n_iters, 3, B, 1, STAMP, STAMP) if self.arch == _lib.ARCH_G else (self.n_iters + 1, 5, B, 1, STAMP, STAMP)
                 ana = torch.empty(shape, device=dev)
             chunk = _chunk_for(B, self.arch)
+            if xdense is not None:
+                xw = xdense._weights(dev)
+                xchunk = xdense._chunk(min(B, chunk))
+                xws, xbytes = _xd_workspace(dev, xchunk)
+                check(lib.gd_admm_forward_xdense(w.handle, xw.handle, llh, int(v0_over_alpha), _ptr(y), _ptr(psf), _ptr(a), _ptr(out), _ptr(rho),
+                                                 _ptr(ana), B, _ptr(ws), nbytes, _ptr(xws), xbytes, xchunk, _stream(dev)))
+                return out, rho, ana
             if ana is None and rho is None and 0 < B <= graph_max_batch() and not torch.cuda.is_current_stream_capturing():
                 return self._graphed(w, y, psf, a, llh, v0_over_alpha, precision, ws, nbytes), None, None
             if ana is None and B > chunk and n_streams() == 2:

@@ -2,8 +2,9 @@
 
 rho1/rho2 ADMM with the auxiliary variable v, circular 48x48 transforms, ResUNet nc = 64..512.  Parity follows the
 code the reference actually executes: the SECOND X_Update definition (:311-319, lhs = rho1*HtH + rho2) shadows the
-first for both classes.  Supported: denoiser='ResUNet', PnP=True (PnP=False is broken in
-the reference itself, :208).  llh='Gaussian' and 'Poisson' are both implemented.
+first for both classes.  Supported: denoiser='ResUNet' and 'XDenseUNet' (:163 -- any string other than
+'ResUNet' selects the XDenseUNet, as in the reference), PnP=True (PnP=False is broken in the reference itself, :208).
+llh='Gaussian' and 'Poisson' are both implemented.
 """
 import torch
 import torch.nn as nn
@@ -12,6 +13,7 @@ from gdeconv import _lib
 from gdeconv.engine import AdmmEngine
 from models.ResUNet import ResUNet
 from models.subnet import SubNetParams
+from models.XDenseUNet import XDenseUNet
 from models.unrolled_admm_gaussian import _Prefixed
 
 
@@ -44,6 +46,17 @@ class Z_Update_ResUNet(nn.Module):
         return self.net(z.float())
 
 
+class Z_Update_XDenseUNet(nn.Module):
+    """reference :142-151 / :360-369: z = XDenseUNet(z) (fp32, csrc/xdense.cu)."""
+
+    def __init__(self):
+        super().__init__()
+        self.net = XDenseUNet()
+
+    def forward(self, z):
+        return self.net(z.float())
+
+
 class _Fused(nn.Module):
     def forward(self, *args, **kwargs):
         raise NotImplementedError('gdeconv: this update is fused into gd_admm_forward; call the ADMM module')
@@ -62,8 +75,17 @@ class V_Update_Poisson(_Fused):
 
 
 def _check(denoiser, PnP):
-    if denoiser != 'ResUNet' or not PnP:
-        raise NotImplementedError("gdeconv: Unrolled_ADMM supports denoiser='ResUNet', PnP=True only")
+    if not PnP:
+        raise NotImplementedError('gdeconv: Unrolled_ADMM supports PnP=True only (PnP=False fails in the reference itself, :208)')
+
+
+def _z_update(denoiser):
+    return Z_Update_ResUNet() if denoiser == 'ResUNet' else Z_Update_XDenseUNet()          # reference :163 / :381
+
+
+def _xdense_of(module):
+    """the XDenseEngine of the module's Z-update, or None when the denoiser is the ResUNet"""
+    return None if module.denoiser == 'ResUNet' else module.Z.net._engine[0]
 
 
 class Unrolled_ADMM(nn.Module):
@@ -73,7 +95,7 @@ class Unrolled_ADMM(nn.Module):
         self.n, self.llh, self.PnP, self.subnet, self.denoiser = n_iters, llh, PnP, subnet, denoiser
         self.X = X_Update()
         self.V = V_Update_Poisson() if llh == 'Poisson' else V_Update_Gaussian()
-        self.Z = Z_Update_ResUNet()
+        self.Z = _z_update(denoiser)
         if self.subnet:
             self.init = SubNet(self.n)
         else:
@@ -86,7 +108,7 @@ class Unrolled_ADMM(nn.Module):
         return _lib.LLH_POISSON if self.llh == 'Poisson' else _lib.LLH_GAUSSIAN
 
     def forward(self, y, kernel, alpha):
-        out, _, _ = self._engine[0].admm(y, kernel, alpha, llh=self._llh(), precision=self.precision)
+        out, _, _ = self._engine[0].admm(y, kernel, alpha, llh=self._llh(), precision=self.precision, xdense=_xdense_of(self))
         return out                                   # x_list[-1] (* alpha for Poisson), :215
 
 
@@ -110,7 +132,7 @@ class Unrolled_ADMM_Old(nn.Module):
         self.n, self.llh, self.PnP, self.SubNet, self.denoiser = n_iters, llh, PnP, SubNet, denoiser
         self.X = X_Update()
         self.V = V_Update_Poisson() if llh == 'Poisson' else V_Update_Gaussian()
-        self.Z = Z_Update_ResUNet()
+        self.Z = _z_update(denoiser)
         self.precision = None
         if self.SubNet:
             self.init = InitNet(self.n)
@@ -124,6 +146,6 @@ class Unrolled_ADMM_Old(nn.Module):
     def forward(self, y, kernel, alpha):
         llh = _lib.LLH_POISSON if self.llh == 'Poisson' else _lib.LLH_GAUSSIAN
         _, _, ana = self._engine[0].admm(y, kernel, alpha, llh=llh, v0_over_alpha=True, want_analysis=True,
-                                         precision=self.precision)
+                                         precision=self.precision, xdense=_xdense_of(self))
         lists = [[ana[i, q] for i in range(self.n + 1)] for q in range(5)]          # v, z, x, u1, u2 (:419-442)
         return (*lists, alpha)

@@ -137,6 +137,15 @@ GD_API int gd_xdense_forward(const GdXDense* x, const float* in, float* out, int
 GD_API int gd_tikhonet_forward(const GdXDense* x, int filter, float lam, const float* y, const float* psf, const float* alpha,
                                float* out, int batch, void* workspace, size_t workspace_bytes, int chunk, void* stream);
 
+/* Replaces Unrolled_ADMM(_Old).forward / ADMMNet.forward constructed with denoiser='XDenseUNet' (models/Unrolled_ADMM.py:142-151,163,
+ * 360-369,381; models/ADMMNet.py:65-74,87): the path-U loop of gd_admm_forward with z = XDenseUNet(x + u1) as the Z-update (fp32, on
+ * the unscaled input).  `w` is packed with gd_pack_weights(GD_ARCH_U, ...) from the same state_dict and carries the SubNet or the
+ * rho parameters (a ResUNet is not needed); `x` is packed with gd_pack_xdense(prefix "Z.net.").  Arguments as gd_admm_forward
+ * (`flags` = its u_v0_over_alpha word) plus the XDenseUNet workspace of gd_xdense_workspace_bytes(xd_chunk). */
+GD_API int gd_admm_forward_xdense(const GdWeights* w, const GdXDense* x, int llh, int flags, const float* y, const float* psf,
+                                  const float* alpha, float* out, float* rho_out, float* analysis, int batch, void* workspace,
+                                  size_t workspace_bytes, void* xd_workspace, size_t xd_workspace_bytes, int xd_chunk, void* stream);
+
 /* Test hook: one tap-GEMM layer of the denoiser on caller-packed operands (layouts of csrc/gd_common.cuh:
  * activations [Kt/CH][Ptot][CH], CH = 8 halves (fp16 modes) or 4 floats; weights as gd_pack_weights lays them out
  * for `precision`; out32 [N/4][Ptot][4] fp32).  ntaps = 9 (3x3, zero padding) or 1.  `geom7` receives

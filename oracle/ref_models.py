@@ -238,17 +238,28 @@ class UnrolledADMMGaussian(nn.Module):
 # --------------------------------------------------------------------------
 
 
+class _ZXDense(nn.Module):
+    """Z_Update_XDenseUNet (models/Unrolled_ADMM.py:142-151, models/ADMMNet.py:65-74): z = XDenseUNet(z.float())."""
+
+    def __init__(self):
+        super().__init__()
+        self.net = XDenseUNet()
+
+    def forward(self, z):
+        return self.net(z.float())
+
+
 class Unrolled_ADMM(nn.Module):
     """models/Unrolled_ADMM.py:153-215 with the *effective* X_Update of :311-319
     (``lhs = rho1*HtH + rho2``; the second definition shadows the first, SURVEY.md
     section 0.4), V_Update_Gaussian :331-336 / V_Update_Poisson :322-328 and
-    Z_Update_ResUNet :349-357 (nc 64..512)."""
+    Z_Update_ResUNet :349-357 (nc 64..512) or, for any other ``denoiser`` string, Z_Update_XDenseUNet :142-151 (:163)."""
 
     def __init__(self, n_iters=8, llh='Poisson', denoiser='ResUNet', PnP=True, subnet=True):
         super().__init__()
-        assert denoiser == 'ResUNet' and PnP, "oracle covers the PnP ResUNet path only"
-        self.n, self.llh, self.subnet = n_iters, llh, subnet
-        self.Z = _ZNet([64, 128, 256, 512])
+        assert PnP, "oracle covers the PnP path only (PnP=False fails in the reference itself)"
+        self.n, self.llh, self.subnet, self.denoiser = n_iters, llh, subnet, denoiser
+        self.Z = _ZNet([64, 128, 256, 512]) if denoiser == 'ResUNet' else _ZXDense()
         if subnet:
             self.init = SubNet(2 * n_iters)
         else:
@@ -321,6 +332,9 @@ class ADMMNet(Unrolled_ADMM):
         super().__init__(n_iters, llh, denoiser, PnP, subnet=False)
         del self.rho1_iters, self.rho2_iters
         self.rho1_iters, self.rho2_iters = torch.full((n_iters,), 0.5), torch.full((n_iters,), 0.5)
+        if denoiser != 'ResUNet':                     # :65-74: no try/except around the XDenseUNet file
+            self.Z.net.load_state_dict(torch.load(model_file, map_location='cpu'))
+            return
         try:
             self.Z.net.load_state_dict(torch.load(model_file, map_location='cpu'))
         except Exception:

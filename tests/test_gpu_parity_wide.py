@@ -233,4 +233,43 @@ def test_admmnet_and_old_without_subnet(golden, dev, tmp_path, monkeypatch):
     with pytest.raises(ValueError):
         ADMMNet(2, model_file=str(tmp_path / 'missing.pth'))
     with pytest.raises(NotImplementedError):
-        ADMMNet(2, denoiser='XDenseUNet', model_file=f)
+        ADMMNet(2, PnP=False, model_file=f)
+
+
+def test_xdenseunet_as_admm_denoiser(golden, dev, tmp_path):
+    """denoiser='XDenseUNet' (models/Unrolled_ADMM.py:142-151,163,381; models/ADMMNet.py:65-74,87) through gd_admm_forward_xdense, with
+    the reference's TRAINED XDenseUNet as the Z-update, against the outputs of the REAL reference (tests/golden/xdense_admm_v1.pt).
+    The whole path is fp32 (FFT kernels + csrc/xdense.cu), so the internal fp32 gate applies, not the 1e-3 product tolerance."""
+    from conftest import ROOT
+    from models.ADMMNet import ADMMNet
+    from models.Unrolled_ADMM import Unrolled_ADMM, Unrolled_ADMM_Old
+    gx = torch.load(os.path.join(ROOT, 'tests', 'golden', 'xdense_admm_v1.pt'))
+    tik = torch.load(os.path.join(ROOT, 'tests', 'golden', 'tikhonet_v1.pt'))['state']['Laplacian']
+    xsd = {k[len('denoiser.'):]: v for k, v in tik.items() if k.startswith('denoiser.')}
+    i = golden['inputs']
+    y, k, a = i['y'][:2].to(dev), i['psf'][:2].to(dev), i['alpha'][:2].to(dev)
+    TOL32 = 2e-4
+    cases = {'U2_gauss_xd': (Unrolled_ADMM, dict(n_iters=2, llh='Gaussian', denoiser='XDenseUNet')),
+             'U2_poisson_xd_norho': (Unrolled_ADMM, dict(n_iters=2, llh='Poisson', denoiser='XDenseUNet', subnet=False)),
+             'UOld2_gauss_xd': (Unrolled_ADMM_Old, dict(n_iters=2, llh='Gaussian', denoiser='XDenseUNet'))}
+    for name, (cls, kw) in cases.items():
+        m = cls(**kw).eval()
+        sd = dict(gx['state'][name])
+        sd.update({'Z.net.' + kk: v for kk, v in xsd.items()})
+        assert set(sd) == set(m.state_dict()), name                         # the reference's key layout
+        m.load_state_dict(sd)
+        m = m.to(dev)
+        out = m(y, k, a)
+        if isinstance(out, tuple):
+            for got, want in zip([t[-1] for t in out[:5]], gx['out'][name]):
+                assert rel_l2(got.cpu(), want).max() < TOL32, name
+        else:
+            assert rel_l2(out.cpu(), gx['out'][name]).max() < TOL32, name
+            # a ragged multi-chunk batch gives the same per-stamp result as the two-stamp call
+            big = m(y.repeat(40, 1, 1, 1)[:75], k.repeat(40, 1, 1, 1)[:75], a.repeat(40, 1, 1, 1)[:75])
+            assert torch.equal(big[:2], out) and torch.equal(big[72:74], out)
+    f = str(tmp_path / 'xdense.pth')
+    torch.save(xsd, f)
+    for llh in ('Gaussian', 'Poisson'):
+        m = ADMMNet(2, llh=llh, denoiser='XDenseUNet', model_file=f).eval().to(dev)
+        assert rel_l2(m(y, k, a).cpu(), gx['out'][f'ADMMNet2_{llh}_xd']).max() < TOL32, llh

@@ -77,7 +77,10 @@ def test_unsupported_configurations_raise():
     with pytest.raises(NotImplementedError):
         UnrolledADMMGaussian(2, PnP=False)
     with pytest.raises(NotImplementedError):
-        Unrolled_ADMM(2, denoiser='XDenseUNet')
+        Unrolled_ADMM(2, PnP=False)
+    # denoiser='XDenseUNet' is supported: same state_dict keys as the reference's Z_Update_XDenseUNet (models/Unrolled_ADMM.py:142-151)
+    import oracle.ref_models as O
+    assert list(Unrolled_ADMM(2, denoiser='XDenseUNet').state_dict().keys()) == list(O.Unrolled_ADMM(2, denoiser='XDenseUNet').state_dict().keys())
     with pytest.raises(NotImplementedError):
         ResUNet(nc=[16, 32, 64, 128])
 

@@ -113,6 +113,33 @@ def test_admmnet_and_old_without_subnet(tmp_path):
         assert rel_l2(got, want).max() < TOL
 
 
+def test_xdenseunet_as_admm_denoiser(tmp_path):
+    """oracle ADMM classes with denoiser='XDenseUNet' (models/Unrolled_ADMM.py:142-151,163; models/ADMMNet.py:65-74,87) vs the outputs of
+    the REAL reference with its trained XDenseUNet as the Z-update (tests/golden/make_golden_xdense_admm.py, bit-exact at generation)"""
+    g = torch.load(os.path.join(ROOT, 'tests', 'golden', 'golden_v1.pt'))
+    gx = torch.load(os.path.join(ROOT, 'tests', 'golden', 'xdense_admm_v1.pt'))
+    tik = torch.load(os.path.join(ROOT, 'tests', 'golden', 'tikhonet_v1.pt'))['state']['Laplacian']
+    xsd = {k[len('denoiser.'):]: v for k, v in tik.items() if k.startswith('denoiser.')}
+    y, k, a = (t[:2] for t in _inputs(g))
+    m = O.Unrolled_ADMM(2, llh='Gaussian', denoiser='XDenseUNet').eval()
+    sd = dict(gx['state']['U2_gauss_xd']); sd.update({'Z.net.' + kk: v for kk, v in xsd.items()})
+    m.load_state_dict(sd)
+    with torch.no_grad():
+        assert rel_l2(m(y, k, a), gx['out']['U2_gauss_xd']).max() < TOL
+    f = str(tmp_path / 'xdense.pth')
+    torch.save(xsd, f)
+    with torch.no_grad():
+        out = O.ADMMNet(2, llh='Poisson', denoiser='XDenseUNet', model_file=f).eval()(y, k, a)
+    assert rel_l2(out, gx['out']['ADMMNet2_Poisson_xd']).max() < TOL
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='reference checkout not mounted')
+def test_xdense_admm_golden_vs_live_reference():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'golden', 'make_golden_xdense_admm.py'), '--check'],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, PYTHONDONTWRITEBYTECODE='1'))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='reference checkout not mounted')
 def test_admmnet_golden_vs_live_reference():
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'golden', 'make_golden_admmnet.py'), '--check'],
