@@ -3,6 +3,7 @@
 #   gpurun --timeout 3000 -- 'bash tools/gpu/r2_round_end.sh tests'    full GPU test suite, smoke, headline bench + reference arm, configs 1-2, parity margins
 #   gpurun --timeout 1500 -- 'bash tools/gpu/r2_round_end.sh list'     ncu launch list of one steady-state step
 #   gpurun --timeout 1500 -- 'bash tools/gpu/r2_round_end.sh layers'   per-launch metrics of one denoiser call
+#   gpurun --timeout 1500 -- 'bash tools/gpu/r2_round_end.sh solver'   stamps/s of the classical solvers alone + one --set full capture of k_solver (Wiener)
 #   gpurun --timeout 1500 -- 'bash tools/gpu/r2_round_end.sh full'     one --set full capture (source-level) of the four chain-kernel launches
 mkdir -p gpurun_out
 BCMD="python bench.py --steps 1 --warmup 3 --stamps 5000 --no-cpu-baseline"
@@ -26,5 +27,9 @@ layers)
 full)
   timeout 600 $BCMD > gpurun_out/plain3.log 2>&1 && \
   timeout 1200 ncu --set full --import-source on --clock-control none -k regex:"k_l1_chain|k_l2_chain" -s 8 -c 4 -o gpurun_out/full_chain -f $BCMD > gpurun_out/ncu3.log 2>&1; echo "ncu full rc=$?"
+  ;;
+solver)
+  timeout 600 python tools/gpu/solver_probe.py > gpurun_out/solver_probe.jsonl 2> gpurun_out/solver_probe.err; echo "probe rc=$?"; cat gpurun_out/solver_probe.jsonl
+  [ -s gpurun_out/solver_probe.jsonl ] && timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_solver" -s 1 -c 1 -o gpurun_out/full_solver -f python tools/gpu/solver_probe.py > gpurun_out/ncu4.log 2>&1; echo "ncu solver rc=$?"
   ;;
 esac
