@@ -74,6 +74,14 @@ template <> struct TwC<16> {
     }
 };
 
+template <> struct TwC<48> {          // m in [0, 30]: the twiddles n2*k1 of the 3 x 16 split
+    GD_HD static float2 w(int m) {
+        constexpr float c[31] = {1.f, 0.99144486137381038f, 0.96592582628906831f, 0.92387953251128674f, 0.86602540378443871f, 0.79335334029123517f, 0.70710678118654757f, 0.60876142900872066f, 0.5f, 0.38268343236508984f, 0.25881904510252074f, 0.13052619222005171f, 0.f, -0.1305261922200516f, -0.25881904510252063f, -0.3826834323650895f, -0.5f, -0.60876142900872066f, -0.70710678118654746f, -0.79335334029123505f, -0.86602540378443871f, -0.92387953251128674f, -0.9659258262890682f, -0.99144486137381038f, -1.f, -0.99144486137381038f, -0.96592582628906831f, -0.92387953251128685f, -0.86602540378443882f, -0.79335334029123517f, -0.70710678118654791f};
+        constexpr float s[31] = {0.f, -0.13052619222005157f, -0.25881904510252074f, -0.38268343236508978f, -0.5f, -0.60876142900872066f, -0.70710678118654746f, -0.79335334029123517f, -0.8660254037844386f, -0.92387953251128674f, -0.96592582628906831f, -0.99144486137381038f, -1.f, -0.99144486137381038f, -0.96592582628906831f, -0.92387953251128685f, -0.86602540378443871f, -0.79335334029123517f, -0.70710678118654757f, -0.60876142900872088f, -0.5f, -0.38268343236508989f, -0.25881904510252102f, -0.13052619222005199f, 0.f, 0.13052619222005177f, 0.25881904510252079f, 0.38268343236508967f, 0.5f, 0.60876142900872066f, 0.70710678118654713f};
+        return make_float2(c[m], s[m]);
+    }
+};
+
 // ---- in-register forward DFT codelets, natural order in and out ----
 template <int R> struct Dft;
 
@@ -132,6 +140,26 @@ template <> struct Dft<6> : DftComposite<2, 3> {};
 template <> struct Dft<8> : DftComposite<2, 4> {};
 template <> struct Dft<12> : DftComposite<3, 4> {};
 template <> struct Dft<16> : DftComposite<4, 4> {};
+
+// ---- whole 48-point forward DFT in the registers of ONE thread (3 x 16 Cooley-Tukey, every index a compile-time constant) ----
+// in: v[n] natural order;  out: frequency k is in v[Fft48::reg(k)]  (v[16*k1 + k2] = X[k1 + 3*k2]).
+// The inverse uses idft(X) = conj(dft(conj(X))) (unscaled), i.e. conjugate on the way in and out.
+struct Fft48 {
+    GD_HD static constexpr int reg(int k) { return 16 * (k % 3) + k / 3; }
+    GD_HD static void run(float2* v) {
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) {
+            float2 a[3] = {v[n2], v[16 + n2], v[32 + n2]};
+            Dft<3>::run(a);
+            v[n2] = a[0];
+            v[16 + n2] = n2 ? cmul(a[1], TwC<48>::w(n2)) : a[1];
+            v[32 + n2] = n2 ? cmul(a[2], TwC<48>::w(2 * n2)) : a[2];
+        }
+        Dft<16>::run(v);
+        Dft<16>::run(v + 16);
+        Dft<16>::run(v + 32);
+    }
+};
 
 // ---- two-pass length-N transform on one line held in (shared) memory ----
 // tw[m] = exp(-2 pi i m / N), m in [0, N)

@@ -14,8 +14,12 @@
 #include "conv_epilogue.cuh"
 #include "fft_block.cuh"
 #include "launch.cuh"
+#include "umma_ptx.cuh"
 
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 namespace gd {
 
@@ -330,6 +334,141 @@ __global__ void __launch_bounds__(U_THREADS) k_solver(int kind_flags, int n_iter
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Wiener / Tikhonov with every 48-point transform in the REGISTERS of one thread (Fft48, fft_core.cuh): the phase-structured
+// k_solver moves each element through shared memory ~15 times per stamp (5 phases per 2-D transform, 39 % of the wavefronts
+// bank-conflict replays, 76 % of the shared-memory pipe) and spends 2.8 instructions per flop on index arithmetic
+// (profiles/solver_r02.md).  Here a 2-D real transform is
+//   P1   column pass: one thread = columns c and c+24 of y (or of psf) packed as ONE complex column, read straight from global
+//        memory (coalesced), 48-point FFT in registers, split by Hermitian symmetry, rows k1 = 0..24 of the half spectrum -> smem
+//   P23  row pass: one thread = row k1 of one stamp: FFT of the psf row, FFT of the y row, the pointwise solve
+//        conj(H) Y / (|H|^2 + reg) (models/Wiener.py:16-19, models/Tikhonet.py:20-31), and the inverse row FFT
+//   P4   inverse column pass: one thread = output columns n2 and n2+24 as one complex column (rows 25..47 by Hermitian symmetry),
+//        stored straight to global memory (coalesced).
+// Three shared-memory exchanges per stamp, all conflict-free (row stride 49 float2), no index arithmetic inside the transforms.
+constexpr int W48_G = 5;                          // stamps per CTA pass: 25 rows x 5 = 125 row items on 128 threads
+constexpr int W48_THREADS = 128;
+constexpr int W48_ROW = 50;                       // float2 per spectrum row (48 + 2 pad): rows 16-byte aligned for 128-bit accesses,
+                                                  // 100 words = 4 mod 32 keeps the 8 threads of a 128-bit wavefront on distinct banks
+constexpr int W48_PLANE = 25 * W48_ROW;           // rows k1 = 0..24
+constexpr size_t W48_SMEM = (size_t)W48_G * 2 * W48_PLANE * sizeof(float2) + (size_t)W48_PLANE * sizeof(float);
+
+__global__ void __launch_bounds__(W48_THREADS, 2) k_wiener48(int kind_flags, float lam, const float* __restrict__ y,
+                                                             const float* __restrict__ psf, const float* __restrict__ alpha,
+                                                             float* __restrict__ out, int batch, const float* __restrict__ lap_abs2) {
+    const int kind = kind_flags & 0xff;
+    const bool clamp_y = (kind_flags & 0x100) != 0;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* buf = reinterpret_cast<float2*>(smem_raw);                  // [G][2][25][49]: plane 0 = y, plane 1 = psf
+    float* lapS = reinterpret_cast<float*>(buf + W48_G * 2 * W48_PLANE);    // [25][49] |L|^2 of the Laplacian filter (kind 3)
+    if (kind == 3)
+        for (int i = threadIdx.x; i < 25 * 48; i += W48_THREADS) lapS[(i / 48) * W48_ROW + i % 48] = lap_abs2[i];
+    for (int g0 = blockIdx.x * W48_G; g0 < batch; g0 += gridDim.x * W48_G) {
+        const int ng = min(W48_G, batch - g0);
+        {   // the next pass's stamps on their way into L2 while this pass computes (pass 0 reads them with plain loads)
+            const int gn = g0 + gridDim.x * W48_G;
+            if (threadIdx.x < 2 && gn < batch) {
+                const int nn = min(W48_G, batch - gn);
+                bulk_prefetch_l2((threadIdx.x ? psf : y) + (size_t)gn * NPIX, (uint32_t)(nn * NPIX * sizeof(float)));
+            }
+        }
+        // Five passes of (load 48 values, FFT, store) through ONE inlined copy of the transform: with a copy per pass the kernel
+        // is ~90 KB of straight-line code and stalls on instruction fetch more than on anything else (measured: 'no_instruction'
+        // 1.09 warps per issue).  Pass 0 = P1, passes 1-3 = P23 (psf row, y row + solve, inverse row), pass 4 = P4.
+#pragma unroll 1
+        for (int pass = 0; pass < 5; ++pass) {
+            const int per = pass == 0 ? 48 : pass == 4 ? 24 : 25;
+#pragma unroll 1
+            for (int it = threadIdx.x; it < ng * per; it += W48_THREADS) {
+                const int s = it / per, j = it - s * per;
+                float2* yplane = buf + (s * 2) * W48_PLANE;
+                float2 v[48];
+                if (pass == 0) {
+                    const int im = j / 24, c = j - im * 24;
+                    const float* src = (im ? psf : y) + (size_t)(g0 + s) * NPIX + c;
+                    float mul = 1.f;
+                    if (!im && kind != 1) mul = 1.0f / alpha[g0 + s];   // Tikhonov transforms y / alpha (Tikhonet.py:20), Wiener y itself
+                    const bool cl = !im && clamp_y;
+#pragma unroll
+                    for (int n = 0; n < 48; ++n) {
+                        float a = src[n * 48], b = src[n * 48 + 24];
+                        if (cl) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                        v[n] = make_float2(a * mul, b * mul);
+                    }
+                } else if (pass < 4) {
+                    const float4* row = reinterpret_cast<const float4*>(yplane + (pass == 1 ? W48_PLANE : 0) + j * W48_ROW);
+#pragma unroll
+                    for (int c = 0; c < 24; ++c) { const float4 q = row[c]; v[2 * c] = make_float2(q.x, q.y); v[2 * c + 1] = make_float2(q.z, q.w); }
+                } else {
+                    const float2* G = yplane + j;
+#pragma unroll
+                    for (int k1 = 0; k1 <= 24; ++k1) {                            // conj(Ga + i Gb)
+                        const float2 ga = G[k1 * W48_ROW], gb = G[k1 * W48_ROW + 24];
+                        v[k1] = make_float2(ga.x - gb.y, -(ga.y + gb.x));
+                        if (k1 > 0 && k1 < 24) v[48 - k1] = make_float2(ga.x + gb.y, -(gb.x - ga.y));   // rows 48 - k1: conj(conj Ga + i conj Gb)
+                    }
+                }
+                Fft48::run(v);
+                if (pass == 0) {
+                    const int im = j / 24, c = j - im * 24;
+                    float2* plane = yplane + im * W48_PLANE + c;
+#pragma unroll
+                    for (int k = 0; k <= 24; ++k) {                           // W = A + iB, A and B real columns: A(k) = (W(k) + conj W(-k)) / 2
+                        const float2 p = v[Fft48::reg(k)], q = v[Fft48::reg((48 - k) % 48)];
+                        plane[k * W48_ROW] = make_float2(0.5f * (p.x + q.x), 0.5f * (p.y - q.y));
+                        plane[k * W48_ROW + 24] = make_float2(0.5f * (p.y + q.y), 0.5f * (q.x - p.x));  // B(k) = -i (W(k) - conj W(-k)) / 2
+                    }
+                } else if (pass == 1) {
+                    float4* hrow = reinterpret_cast<float4*>(yplane + W48_PLANE + j * W48_ROW);
+#pragma unroll
+                    for (int k2 = 0; k2 < 48; k2 += 2) {
+                        const float2 p = v[Fft48::reg(k2)], q = v[Fft48::reg(k2 + 1)];
+                        hrow[k2 / 2] = make_float4(p.x, p.y, q.x, q.y);
+                    }
+                } else if (pass == 2) {
+                    float4* yrow = reinterpret_cast<float4*>(yplane + j * W48_ROW);
+                    const float4* hrow = reinterpret_cast<const float4*>(yplane + W48_PLANE + j * W48_ROW);
+                    const float a = alpha[g0 + s];
+                    const float reg0 = kind == 1 ? 350.f / a : lam;
+                    const float sg1 = (j & 1) ? -1.f : 1.f;                       // H = (-1)^(k1+k2) Hc (psf_to_otf's roll by 24, 24)
+#pragma unroll
+                    for (int k2 = 0; k2 < 48; k2 += 2) {
+                        const float4 hq = hrow[k2 / 2];
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float2 h = e ? make_float2(hq.z, hq.w) : make_float2(hq.x, hq.y), yy = v[Fft48::reg(k2 + e)];
+                            const float hh = h.x * h.x + h.y * h.y;
+                            const float div = kind == 3 ? hh + lam * lapS[j * W48_ROW + k2 + e] : hh + reg0;
+                            const float2 n = cmul(cconj(h), yy);
+                            const float f = (e ? -sg1 : sg1) / div;                  // k2 + e is odd exactly for e = 1
+                            o[2 * e] = n.x * f; o[2 * e + 1] = -n.y * f;              // conj(X): inverse = conj(dft(conj X))
+                        }
+                        yrow[k2 / 2] = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                } else if (pass == 3) {
+                    float4* yrow = reinterpret_cast<float4*>(yplane + j * W48_ROW);
+#pragma unroll
+                    for (int n2 = 0; n2 < 48; n2 += 2) {
+                        const float2 p = v[Fft48::reg(n2)], q = v[Fft48::reg(n2 + 1)];
+                        yrow[n2 / 2] = make_float4(p.x, -p.y, q.x, -q.y);
+                    }
+                } else {
+                    float* dst = out + (size_t)(g0 + s) * NPIX + j;
+                    const float sc = 1.0f / (48.f * 48.f);
+#pragma unroll
+                    for (int n1 = 0; n1 < 48; ++n1) {
+                        const float2 g = v[Fft48::reg(n1)];
+                        dst[n1 * 48] = g.x * sc;
+                        dst[n1 * 48 + 24] = -g.y * sc;
+                    }
+                }
+            }
+            if (pass == 0 || pass >= 3) __syncthreads();          // passes 1-3 stay in one thread's own rows
+        }
+    }
+}
+
 // conv_fft_batch(H or conj(H), x), utils/utils_torch.py:46-50
 __global__ void __launch_bounds__(U_THREADS) k_conv_fft(const float* __restrict__ x, const float* __restrict__ psf,
                                                         float* __restrict__ out, int adjoint) {
@@ -641,6 +780,7 @@ int fft_kernels_init() {
     if ((rc = opt_in_smem(k_g_xupdate<false>, G_SMEM_XUP))) return rc;
     if ((rc = opt_in_smem(k_g_xupdate<true>, G_SMEM_XUP))) return rc;
     if ((rc = opt_in_smem(k_solver, SOLVER_SMEM))) return rc;
+    if ((rc = opt_in_smem(k_wiener48, W48_SMEM))) return rc;
     if ((rc = opt_in_smem(k_conv_fft, SOLVER_SMEM))) return rc;
     if ((rc = opt_in_smem(k_psf_to_otf, SOLVER_SMEM_LIGHT))) return rc;
     if ((rc = opt_in_smem(k_conv_otf, SOLVER_SMEM_LIGHT))) return rc;
@@ -695,9 +835,58 @@ int launch_fill_rho(const float* src, int n_rho, float* rho, int batch, cudaStre
     GD_LAUNCHED();
     return GD_OK;
 }
+// |L|^2 of the reference's Laplacian filter on the half spectrum k1 in [0, 25), k2 in [0, 48) (lap_quirk_abs2 above, in double)
+static float* g_lap_abs2[16] = {nullptr};
+static int lap_table(float** out) {
+    int dev;
+    GD_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) { set_error("lap_table: device %d out of range", dev); return GD_ECUDA; }
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!g_lap_abs2[dev]) {
+        const int rr[7] = {0, 1, 46, 47, 47, 47, 47}, cc[7] = {47, 47, 47, 0, 1, 46, 47};
+        const double vv[7] = {1, 1, 1, 1, 1, 1, -4};
+        std::vector<float> h(25 * 48);
+        for (int k1 = 0; k1 < 25; ++k1)
+            for (int k2 = 0; k2 < 48; ++k2) {
+                double re = 0, im = 0;
+                for (int i = 0; i < 7; ++i) {
+                    const double ph = -2.0 * 3.14159265358979323846 * ((k1 * rr[i] + k2 * cc[i]) % 48) / 48.0;
+                    re += vv[i] * cos(ph); im += vv[i] * sin(ph);
+                }
+                h[k1 * 48 + k2] = (float)(re * re + im * im);
+            }
+        GD_CUDA_CHECK(cudaMalloc(&g_lap_abs2[dev], h.size() * sizeof(float)));
+        GD_CUDA_CHECK(cudaMemcpy(g_lap_abs2[dev], h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    *out = g_lap_abs2[dev];
+    return GD_OK;
+}
+
+// GDECONV_SOLVER48=0 restores the phase-structured k_solver for Wiener / Tikhonov (Richardson-Lucy always runs in k_solver)
+static int solver48_mode() {
+    static int m = -1;
+    if (m < 0) { const char* e = getenv("GDECONV_SOLVER48"); m = e ? atoi(e) : 1; }
+    return m;
+}
+
 int launch_solver(int kind, int n_iters, float lam, const float* y, const float* psf, const float* alpha, float* out,
                   int batch, cudaStream_t st) {
     if (batch <= 0) return GD_OK;
+    if ((kind & 0xff) != 0 && solver48_mode()) {
+        float* lap = nullptr;
+        if ((kind & 0xff) == 3) { int rc = lap_table(&lap); if (rc != GD_OK) return rc; }
+        static int sms = 0;
+        if (!sms) {
+            int dev;
+            GD_CUDA_CHECK(cudaGetDevice(&dev));
+            GD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const int groups = (batch + W48_G - 1) / W48_G;
+        k_wiener48<<<groups < 2 * sms ? groups : 2 * sms, W48_THREADS, W48_SMEM, st>>>(kind, lam, y, psf, alpha, out, batch, lap);
+        GD_LAUNCHED();
+        return GD_OK;
+    }
     k_solver<<<batch, U_THREADS, (kind & 0xff) == 0 ? SOLVER_SMEM : SOLVER_SMEM_LIGHT, st>>>(kind, n_iters, lam, y, psf, alpha, out);
     GD_LAUNCHED();
     return GD_OK;

@@ -70,3 +70,41 @@ def test_switch_variant_matches_reference(env):
     assert res['finite']
     assert res['golden'] < 1e-3, res          # BASELINE tolerance: relative L2 per stamp
     assert res['big'] < 1e-3, res
+
+
+SOLVER_CHILD = r'''
+import json, os, sys
+ROOT = sys.argv[1]
+sys.path[:0] = [os.path.join(ROOT, 'galaxy-deconv_b200'), ROOT, os.path.join(ROOT, 'tests')]
+import torch
+import oracle.ref_models as O
+from conftest import rel_l2
+from gdsynth import make_batch
+from models.Tikhonet import Tikhonov
+from models.Wiener import Wiener
+dev = torch.device('cuda:0')
+res = {}
+for B in (1, 4, 5, 6, 1483):                      # below, at and above one CTA pass of 5 stamps; many passes per CTA
+    b = make_batch(11, B, 'mixed', device=dev)
+    idx = torch.arange(B) if B < 8 else torch.tensor([0, 4, 5, 741, 1479, 1480, 1482])
+    args = [b[k][idx].cpu() for k in ('obs', 'psf', 'alpha')]
+    for name, mine, ref in (('wiener', lambda: Wiener()(b['obs'], b['psf'], b['alpha']), lambda: O.Wiener()(*args)),
+                            ('tik_id', lambda: Tikhonov('Identity')(b['obs'], b['psf'], b['alpha'], 0.7), lambda: O.Tikhonov('Identity')(*args, 0.7)),
+                            ('tik_lap', lambda: Tikhonov('Laplacian')(b['obs'], b['psf'], b['alpha'], 1.3), lambda: O.Tikhonov('Laplacian')(*args, 1.3))):
+        got = mine()
+        res[name] = max(res.get(name, 0.0), float(rel_l2(got[idx].cpu(), ref()).max()))
+        res['finite'] = res.get('finite', True) and bool(torch.isfinite(got).all())
+print(json.dumps(res))
+'''
+
+
+@pytest.mark.parametrize('env', [{}, {'GDECONV_SOLVER48': '0'}], ids=['register-fft', 'phase-fft'])
+def test_wiener_tikhonov_kernels_match_reference(env):
+    """k_wiener48 (every 48-point transform in one thread's registers, five stamps per CTA pass) and the phase-structured k_solver it
+    replaces, on ragged batches, against the oracle (models/Wiener.py:10-20, models/Tikhonet.py:15-31); internal fp32 gate 2e-5"""
+    r = subprocess.run([sys.executable, '-c', SOLVER_CHILD, ROOT], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res['finite']
+    for k in ('wiener', 'tik_id', 'tik_lap'):
+        assert res[k] < 2e-5, res
