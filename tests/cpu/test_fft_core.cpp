@@ -70,6 +70,26 @@ int main() {
             e = std::max(e, m / 4);
         }
     }
+    {   // the whole 48-point transform of one thread (k_wiener48), forward and through the conjugation identity backward
+        float2 v[48]; cd x[48];
+        for (int n = 0; n < 48; ++n) { x[n] = cd(sin(n * 0.9 + 0.2), cos(n * 1.7) - 0.1); v[n] = make_float2((float)x[n].real(), (float)x[n].imag()); }
+        Fft48::run(v);
+        double m = 0, mx = 0;
+        cd X[48];
+        for (int k = 0; k < 48; ++k) {
+            cd s = 0;
+            for (int n = 0; n < 48; ++n) s += x[n] * std::polar(1.0, -2 * M_PI * n * k / 48);
+            X[k] = s; mx = std::max(mx, std::abs(s));
+            m = std::max(m, std::abs(s - cd(v[Fft48::reg(k)].x, v[Fft48::reg(k)].y)));
+        }
+        float2 w[48];
+        for (int k = 0; k < 48; ++k) w[k] = make_float2(v[Fft48::reg(k)].x, -v[Fft48::reg(k)].y);
+        Fft48::run(w);
+        double mi = 0;
+        for (int n = 0; n < 48; ++n) mi = std::max(mi, std::abs(cd(w[Fft48::reg(n)].x, -w[Fft48::reg(n)].y) / 48.0 - x[n]));
+        printf("Fft48 fwd_rel_err=%.3e inv_abs_err=%.3e\n", m / mx, mi);
+        e = std::max(e, std::max(m / mx, mi));
+    }
     if (e > 5e-6) { printf("FAIL %.3e\n", e); return 1; }
     printf("OK\n");
     return 0;

@@ -77,3 +77,19 @@ def test_row_decode_division_is_exact_up_to_the_largest_admitted_chunk():
             del os.environ['GDECONV_CHUNK']
         else:
             os.environ['GDECONV_CHUNK'] = old
+
+
+def test_fft_core_on_the_host(tmp_path):
+    """csrc/fft_core.cuh is __host__ __device__: the phase functions the kernels run (and the in-register 48-point transform of
+    k_wiener48) are compiled for the host and checked against the DFT definition in double precision (tests/cpu/test_fft_core.cpp)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not found')
+    exe = str(tmp_path / 'test_fft_core')
+    r = subprocess.run([nvcc, '-O1', '-std=c++17', '-Wno-deprecated-gpu-targets', '-I', os.path.join(ROOT, 'galaxy-deconv_b200', 'csrc'),
+                        os.path.join(ROOT, 'tests', 'cpu', 'test_fft_core.cpp'), '-o', exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith('OK'), r.stdout[-2000:]
