@@ -206,7 +206,7 @@ extern "C" int gd_pack_weights(int arch, int n_iters, const GdTensorDesc* tensor
     if (arch != GD_ARCH_G && arch != GD_ARCH_U) GD_FAIL(GD_EUNSUPPORTED, "unknown arch %d", arch);
     if (precision < 0 || precision > 2) GD_FAIL(GD_EUNSUPPORTED, "unknown precision mode %d", precision);
     if (n_iters < 0 || n_iters > 64) GD_FAIL(GD_EBADSHAPE, "n_iters %d out of range", n_iters);
-    GD_CUDA_CHECK(cudaSetDevice(device));
+    GD_DEVICE_SCOPE(device);
     GD_TRY(init_once(device));
     Finder F(tensors, n_tensors);
     GdWeights W;
@@ -342,8 +342,10 @@ extern "C" int gd_pack_weights(int arch, int n_iters, const GdTensorDesc* tensor
 
 extern "C" void gd_free_weights(GdWeights* w) {
     if (!w) return;
-    cudaSetDevice(w->device);
-    cudaFree(w->blob);
+    {
+        gd::DeviceScope scope(w->device);
+        cudaFree(w->blob);
+    }
     delete w;
 }
 
@@ -718,12 +720,19 @@ extern "C" int gd_workspace_init(void* workspace, size_t bytes, int arch, int pr
     return GD_OK;
 }
 
+// Forgets a workspace registered by gd_workspace_init (call before freeing its memory: the allocator may hand the same address to
+// an unrelated buffer, which must not pass gd_admm_forward's workspace check).
+extern "C" void gd_workspace_release(void* workspace) {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    g_ws_reg.erase(workspace);
+}
+
 extern "C" int gd_resunet_forward(const GdWeights* W, const float* in, float* out, int batch, void* workspace,
                                   size_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!W || !W->has_resunet) GD_FAIL(GD_EBADSHAPE, "weights hold no ResUNet");
     if (batch < 0 || (batch && (!in || !out))) GD_FAIL(GD_EBADSHAPE, "gd_resunet_forward: bad batch or NULL buffers");
-    GD_CUDA_CHECK(cudaSetDevice(W->device));
+    GD_DEVICE_SCOPE(W->device);
     Ws ws; int chunk;
     GD_TRY(ws_check(workspace, workspace_bytes, W, &ws, &chunk));
     for (int c0 = 0; c0 < batch; c0 += chunk) {
@@ -738,7 +747,7 @@ extern "C" int gd_subnet_forward(const GdWeights* W, const float* psf, const flo
                                  void* stream) {
     if (!W || !W->has_subnet) GD_FAIL(GD_EBADSHAPE, "weights hold no SubNet");
     if (batch < 0 || (batch && (!psf || !alpha || !rho_out))) GD_FAIL(GD_EBADSHAPE, "gd_subnet_forward: bad batch or NULL buffers");
-    GD_CUDA_CHECK(cudaSetDevice(W->device));
+    GD_DEVICE_SCOPE(W->device);
     return launch_subnet(W->sub, psf, alpha, rho_out, batch, (cudaStream_t)stream);
 }
 
@@ -775,7 +784,7 @@ extern "C" int gd_admm_forward(const GdWeights* W, int llh, int u_v0_over_alpha,
     if (!W || !W->has_resunet) GD_FAIL(GD_EBADSHAPE, "weights hold no ResUNet");
     if (batch < 0 || (batch && (!y || !psf || !alpha || !out))) GD_FAIL(GD_EBADSHAPE, "gd_admm_forward: bad batch or NULL buffers");
     if (llh != GD_LLH_GAUSSIAN && llh != GD_LLH_POISSON) GD_FAIL(GD_EUNSUPPORTED, "unknown likelihood %d", llh);
-    GD_CUDA_CHECK(cudaSetDevice(W->device));
+    GD_DEVICE_SCOPE(W->device);
     Ws ws; int chunk;
     GD_TRY(ws_check(workspace, workspace_bytes, W, &ws, &chunk));
     const int n = W->n_iters, nr = W->n_rho;
@@ -821,7 +830,7 @@ extern "C" int gd_admm_forward_xdense(const GdWeights* W, const GdXDense* X, int
     if (W->arch != GD_ARCH_U) GD_FAIL(GD_EUNSUPPORTED, "the XDenseUNet denoiser exists for Unrolled_ADMM / ADMMNet (arch U) only");
     if (batch < 0 || (batch && (!y || !psf || !alpha || !out))) GD_FAIL(GD_EBADSHAPE, "gd_admm_forward_xdense: bad batch or NULL buffers");
     if (llh != GD_LLH_GAUSSIAN && llh != GD_LLH_POISSON) GD_FAIL(GD_EUNSUPPORTED, "unknown likelihood %d", llh);
-    GD_CUDA_CHECK(cudaSetDevice(W->device));
+    GD_DEVICE_SCOPE(W->device);
     Ws ws; int chunk;
     GD_TRY(ws_check(workspace, workspace_bytes, W, &ws, &chunk));
     const int nr = W->n_rho;

@@ -138,4 +138,22 @@ void set_error(const char* fmt, ...);
         }                                                                                           \
     } while (0)
 
+// Makes `device` current for the scope and restores the caller's device on exit: the C-ABI entry points (and the free functions,
+// which Python runs from __del__ at arbitrary points) must not change the current device of a multi-GPU process behind its back.
+struct DeviceScope {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceScope(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;                      // nothing to restore
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
+#define GD_DEVICE_SCOPE(device)           \
+    gd::DeviceScope _gd_dev_scope(device); \
+    GD_CUDA_CHECK(_gd_dev_scope.err)
+
 }  // namespace gd

@@ -267,7 +267,8 @@ extern "C" GD_API int gd_pack_xdense(const GdTensorDesc* tensors, int n_tensors,
     if (!rc) rc = pack_pw(X->up[2], "up2.1.net.0", "", 352, 60, true);
     if (!rc) rc = pack_pw(X->outc, "output.1", "", 220, 1, true);
     if (rc) { delete X; return rc; }
-    cudaError_t e = cudaSetDevice(device);
+    gd::DeviceScope scope(device);
+    cudaError_t e = scope.err;
     if (e == cudaSuccess) e = cudaMalloc(&X->blob, B.h.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(X->blob, B.h.data(), B.h.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { gd::set_error("gd_pack_xdense: %s", cudaGetErrorString(e)); delete X; return GD_ECUDA; }
@@ -278,8 +279,10 @@ extern "C" GD_API int gd_pack_xdense(const GdTensorDesc* tensors, int n_tensors,
 
 extern "C" GD_API void gd_free_xdense(GdXDense* x) {
     if (!x) return;
-    cudaSetDevice(x->device);
-    cudaFree(x->blob);
+    {
+        gd::DeviceScope scope(x->device);
+        cudaFree(x->blob);
+    }
     delete x;
 }
 
@@ -351,7 +354,7 @@ static int xd_run(const GdXDense* X, int filter, float lam, const float* y, cons
                   const float* out_scale, int batch, void* ws, size_t ws_bytes, int chunk, cudaStream_t st) {
     if (!X) XD_FAIL("XDenseUNet weights are NULL");
     if (batch < 0 || chunk < 1 || !ws || ws_bytes < gd_xdense_workspace_bytes(chunk)) { gd::set_error("XDenseUNet: workspace too small for chunk %d", chunk); return GD_EWORKSPACE; }
-    GD_CUDA_CHECK(cudaSetDevice(X->device));
+    GD_DEVICE_SCOPE(X->device);
     float* base = (float*)ws;
     float* buf[XD_NBUF];
     for (int i = 0; i < XD_NBUF; ++i) { buf[i] = base; base += (size_t)chunk * xd_buf_floats(i); }

@@ -17,7 +17,7 @@ SOLVER_RL, SOLVER_WIENER, SOLVER_TIKHONOV_ID, SOLVER_TIKHONOV_LAP = 0, 1, 2, 3
 PRECISIONS = {'fp32_simt': PREC_FP32_SIMT, 'fp16_umma': PREC_FP16_UMMA, 'fp16_simt': PREC_FP16_SIMT}
 
 #: every symbol include/gdeconv.h declares (tests/test_abi.py checks the header against this list and the .so)
-SYMBOLS = ('gd_version', 'gd_last_error', 'gd_pack_weights', 'gd_free_weights', 'gd_workspace_bytes', 'gd_workspace_init',
+SYMBOLS = ('gd_version', 'gd_last_error', 'gd_pack_weights', 'gd_free_weights', 'gd_workspace_bytes', 'gd_workspace_init', 'gd_workspace_release',
            'gd_admm_forward', 'gd_resunet_forward', 'gd_subnet_forward', 'gd_fft_solver', 'gd_conv_fft', 'gd_moments_e',
            'gd_launch_count', 'gd_debug_geom', 'gd_debug_tapgemm', 'gd_profile_begin', 'gd_profile_end', 'gd_pack_xdense', 'gd_free_xdense', 'gd_xdense_workspace_bytes',
            'gd_xdense_forward', 'gd_tikhonet_forward', 'gd_admm_forward_xdense', 'gd_psf_to_otf', 'gd_conv_otf', 'gd_max_chunk', 'gd_debug_divmagic')
@@ -48,6 +48,8 @@ def _load():
     lib.gd_workspace_bytes.argtypes = [i, i, i]
     lib.gd_workspace_bytes.restype = sz
     lib.gd_workspace_init.argtypes = [vp, sz, i, i, i, vp]
+    lib.gd_workspace_release.argtypes = [vp]
+    lib.gd_workspace_release.restype = None
     lib.gd_admm_forward.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp, i, vp, sz, vp]
     lib.gd_resunet_forward.argtypes = [vp, vp, vp, i, vp, sz, vp]
     lib.gd_subnet_forward.argtypes = [vp, vp, vp, vp, i, vp]

@@ -98,8 +98,24 @@ def _chunk_for(batch, arch=_lib.ARCH_G):
     return min(-(-per // 256) * 256, max(cap, 256))
 
 
+class _WsRelease:
+    """Rides on a workspace tensor: unregisters the workspace from the library when the tensor object dies, i.e. before its
+    memory can go back to the allocator and be handed to an unrelated buffer at the same address."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            lib.gd_workspace_release(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
 def _workspace(device, arch, prec, chunk, slot=0):
-    key = (device.index, arch, prec, chunk, slot)
+    """Scratch memory for `chunk` stamps.  Keyed by the CURRENT STREAM as well: kernels of one stream are ordered, two streams (or two
+    host threads driving different streams) must not share activations, and nothing else orders them."""
+    key = (device.index, arch, prec, chunk, slot, torch.cuda.current_stream(device).cuda_stream)
     with _ws_lock:
         hit = _ws_cache.get(key)
         if hit is not None:
@@ -117,6 +133,7 @@ def _workspace(device, arch, prec, chunk, slot=0):
                 del _ws_cache[k]
         buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         check(lib.gd_workspace_init(_ptr(buf), nbytes, arch, prec, chunk, _stream(device)))
+        buf._gd_release = _WsRelease(buf.data_ptr())
         _ws_cache[key] = (buf, nbytes)
         return buf, nbytes
 

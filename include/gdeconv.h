@@ -74,6 +74,8 @@ GD_API void gd_free_weights(GdWeights* w);
 GD_API size_t gd_workspace_bytes(int arch, int precision, int chunk);
 /* Zeroes the activation halos and writes the header gd_admm_forward validates.  Once per workspace. */
 GD_API int gd_workspace_init(void* workspace, size_t bytes, int arch, int precision, int chunk, void* stream);
+/* Forgets an initialised workspace; call it before freeing the memory (a later allocation may reuse the address). */
+GD_API void gd_workspace_release(void* workspace);
 
 /* Replaces UnrolledADMMGaussian.forward (models/unrolled_admm_gaussian.py:117-152) for arch G and
  * Unrolled_ADMM.forward / Unrolled_ADMM_Old.forward (models/Unrolled_ADMM.py:177-215,396-442) for arch U.
