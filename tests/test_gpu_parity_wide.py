@@ -273,3 +273,24 @@ def test_xdenseunet_as_admm_denoiser(golden, dev, tmp_path):
     for llh in ('Gaussian', 'Poisson'):
         m = ADMMNet(2, llh=llh, denoiser='XDenseUNet', model_file=f).eval().to(dev)
         assert rel_l2(m(y, k, a).cpu(), gx['out'][f'ADMMNet2_{llh}_xd']).max() < TOL32, llh
+
+
+def test_two_streams_do_not_share_scratch(dev, monkeypatch):
+    """Workspaces are keyed by the current stream (gdeconv/engine.py::_workspace): two different batches driven concurrently on two
+    streams give, bit for bit, what each gives alone.  With one shared scratch buffer the activations of the two calls would mix."""
+    from gdsynth import make_batch
+    from models.unrolled_admm_gaussian import UnrolledADMMGaussian
+    monkeypatch.setenv('GDECONV_PRECISION', 'fp16_umma')
+    torch.manual_seed(5)
+    m = UnrolledADMMGaussian(2).eval().to(dev)
+    a, b = make_batch(0, 700, 'mixed', device=dev), make_batch(5000, 700, 60.0, device=dev)
+    want_a, want_b = m(a['obs'], a['psf'], a['alpha']).clone(), m(b['obs'], b['psf'], b['alpha']).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            got_a = m(a['obs'], a['psf'], a['alpha'])
+        with torch.cuda.stream(s2):
+            got_b = m(b['obs'], b['psf'], b['alpha'])
+        torch.cuda.synchronize()
+        assert torch.equal(got_a, want_a) and torch.equal(got_b, want_b)
