@@ -469,6 +469,130 @@ __global__ void __launch_bounds__(W48_THREADS, 2) k_wiener48(int kind_flags, flo
     }
 }
 
+// Richardson-Lucy (models/Richard_Lucy.py:10-24) on the same register-resident transforms: per iteration
+//   Hx = irfft2(rfft2(x) H),  num = irfft2(rfft2(y / Hx) conj H),  x <- x num / div,   div = conj(H[0,0]) (:22, loop-invariant)
+// With five stamps per CTA pass every thread owns ONE column item (columns c, c+24 of one stamp: 120 items) and ONE row item (row k1
+// of one stamp's half spectrum: 125 items) for the whole loop, so an inverse column transform, the pointwise step in image space
+// (y / Hx, or the x update) and the next forward column transform chain in one thread's registers, and so do a forward row
+// transform, the multiplication by H or conj H and the inverse row transform.  Four barriers and 196 transforms per iteration;
+// x lives in `out` (L2-resident between iterations), y is re-read from global memory, the planes are those of k_wiener48.
+// The loop below runs ONE inlined copy of the transform; `kind` selects what happens before and after it.
+__global__ void __launch_bounds__(W48_THREADS, 2) k_rl48(int n_iters, const float* __restrict__ y, const float* __restrict__ psf,
+                                                         float* __restrict__ out, int batch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* buf = reinterpret_cast<float2*>(smem_raw);                  // [G][2][25][ROW]: plane 0 = work, plane 1 = H (sign folded in)
+    float* divS = reinterpret_cast<float*>(buf + W48_G * 2 * W48_PLANE);
+    const int tid = threadIdx.x;
+    const int sc_ = tid / 24, cc = tid - sc_ * 24;                      // column item
+    const int sr = tid / 25, jr = tid - sr * 25;                        // row item
+    const float sc = 1.0f / (48.f * 48.f);
+    const int nsteps = n_iters > 0 ? 2 + 8 * n_iters : 3;               // 3 prologue steps + 8 per iteration - the last iteration's split
+    for (int g0 = blockIdx.x * W48_G; g0 < batch; g0 += gridDim.x * W48_G) {
+        const int ng = min(W48_G, batch - g0);
+        const bool colv = tid < ng * 24, rowv = tid < ng * 25;
+        float2* cplane = buf + (sc_ * 2) * W48_PLANE + cc;               // this thread's two columns of the work plane
+        float2* wrow = buf + (sr * 2) * W48_PLANE + jr * W48_ROW;        // this thread's row of the work plane
+        float2* hrow = wrow + W48_PLANE;
+        const size_t co = colv ? (size_t)(g0 + sc_) * NPIX + cc : 0;
+        float2 v[48];
+        __syncthreads();                          // the previous pass is done with the planes
+#pragma unroll 1
+        for (int t = 0; t < nsteps; ++t) {
+            const int kind = t < 3 ? t : 3 + ((t - 3) & 7);
+            // kinds: 0 psf columns -> H plane | 1 H rows | 2 y columns -> work plane | 3 / 7 row: forward, times H / conj H
+            //        4 / 8 row: inverse -> work plane | 5 column: inverse -> Hx, y / Hx | 9 column: inverse -> num, x update
+            //        6 / 10 column: forward -> work plane
+            const bool is_col = kind == 0 || kind == 2 || kind == 5 || kind == 6 || kind == 9 || kind == 10;
+            if (is_col ? colv : rowv) {
+                if (kind == 0 || kind == 2) {
+                    const float* src = (kind == 0 ? psf : y) + co;
+#pragma unroll
+                    for (int n = 0; n < 48; ++n) {
+                        float a = src[n * 48], b = src[n * 48 + 24];
+                        if (kind == 2) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); out[co + n * 48] = a; out[co + n * 48 + 24] = b; }   // x0 = y (:17)
+                        v[n] = make_float2(a, b);
+                    }
+                } else if (kind == 1 || kind == 3 || kind == 7) {
+                    const float4* row = reinterpret_cast<const float4*>(kind == 1 ? hrow : wrow);
+#pragma unroll
+                    for (int c = 0; c < 24; ++c) { const float4 q = row[c]; v[2 * c] = make_float2(q.x, q.y); v[2 * c + 1] = make_float2(q.z, q.w); }
+                } else if (kind == 5 || kind == 9) {
+#pragma unroll
+                    for (int k1 = 0; k1 <= 24; ++k1) {                            // conj(Ga + i Gb), rows 48 - k1 by Hermitian symmetry
+                        const float2 ga = cplane[k1 * W48_ROW], gb = cplane[k1 * W48_ROW + 24];
+                        v[k1] = make_float2(ga.x - gb.y, -(ga.y + gb.x));
+                        if (k1 > 0 && k1 < 24) v[48 - k1] = make_float2(ga.x + gb.y, -(gb.x - ga.y));
+                    }
+                }
+                Fft48::run(v);
+                if (kind == 0 || kind == 2 || kind == 6 || kind == 10) {
+                    float2* plane = kind == 0 ? cplane + W48_PLANE : cplane;
+#pragma unroll
+                    for (int k = 0; k <= 24; ++k) {                           // split the packed pair of real columns
+                        const float2 p = v[Fft48::reg(k)], q = v[Fft48::reg((48 - k) % 48)];
+                        plane[k * W48_ROW] = make_float2(0.5f * (p.x + q.x), 0.5f * (p.y - q.y));
+                        plane[k * W48_ROW + 24] = make_float2(0.5f * (p.y + q.y), 0.5f * (q.x - p.x));
+                    }
+                } else if (kind == 1) {
+                    const float sg1 = (jr & 1) ? -1.f : 1.f;                      // H = (-1)^(k1+k2) Hc (psf_to_otf's roll by 24, 24)
+                    float4* hr = reinterpret_cast<float4*>(hrow);
+#pragma unroll
+                    for (int k2 = 0; k2 < 48; k2 += 2) {
+                        const float2 p = v[Fft48::reg(k2)], q = v[Fft48::reg(k2 + 1)];
+                        hr[k2 / 2] = make_float4(sg1 * p.x, sg1 * p.y, -sg1 * q.x, -sg1 * q.y);
+                    }
+                    if (jr == 0) divS[sr] = v[Fft48::reg(0)].x;                   // conv_fft_batch(Ht, ones) = conj(H[0,0]) = sum(psf)
+                } else if (kind == 3 || kind == 7) {
+                    const float cj = kind == 7 ? -1.f : 1.f;                      // times H (Hx) or conj H (numerator)
+                    const float4* hr = reinterpret_cast<const float4*>(hrow);
+                    float2 w[48];
+#pragma unroll
+                    for (int k2 = 0; k2 < 48; k2 += 2) {
+                        const float4 hq = hr[k2 / 2];
+                        const float2 x0 = cmul(v[Fft48::reg(k2)], make_float2(hq.x, cj * hq.y));
+                        const float2 x1 = cmul(v[Fft48::reg(k2 + 1)], make_float2(hq.z, cj * hq.w));
+                        w[k2] = make_float2(x0.x, -x0.y); w[k2 + 1] = make_float2(x1.x, -x1.y);        // conjugate: inverse = conj(dft(conj X))
+                    }
+#pragma unroll
+                    for (int k2 = 0; k2 < 48; ++k2) v[k2] = w[k2];
+                } else if (kind == 4 || kind == 8) {
+                    float4* wr = reinterpret_cast<float4*>(wrow);
+#pragma unroll
+                    for (int n2 = 0; n2 < 48; n2 += 2) {
+                        const float2 p = v[Fft48::reg(n2)], q = v[Fft48::reg(n2 + 1)];
+                        wr[n2 / 2] = make_float4(p.x, -p.y, q.x, -q.y);
+                    }
+                } else if (kind == 5) {
+                    float2 w[48];
+#pragma unroll
+                    for (int n1 = 0; n1 < 48; ++n1) {
+                        const float2 g = v[Fft48::reg(n1)];                       // Hx of columns c, c + 24 (unscaled; second one negated)
+                        const float ya = fmaxf(y[co + n1 * 48], 0.f), yb = fmaxf(y[co + n1 * 48 + 24], 0.f);
+                        // :21.  __fdividef (reciprocal + multiply, 2 ulp): the IEEE division's special-case subroutine is taken for
+                        // every clamped-to-zero pixel and cost more than the transforms (measured: 307 M slow-path calls per launch)
+                        w[n1] = make_float2(__fdividef(ya, g.x * sc), __fdividef(yb, -g.y * sc));
+                    }
+#pragma unroll
+                    for (int n1 = 0; n1 < 48; ++n1) v[n1] = w[n1];
+                } else {                                                          // kind 9
+                    const float rdiv = sc / divS[sc_];                            // 1 / (2304 div): one division per thread and iteration
+                    float2 w[48];
+#pragma unroll
+                    for (int n1 = 0; n1 < 48; ++n1) {
+                        const float2 g = v[Fft48::reg(n1)];
+                        const float xa = out[co + n1 * 48] * (g.x * rdiv), xb = out[co + n1 * 48 + 24] * (-g.y * rdiv);     // :23
+                        out[co + n1 * 48] = xa; out[co + n1 * 48 + 24] = xb;
+                        w[n1] = make_float2(xa, xb);
+                    }
+#pragma unroll
+                    for (int n1 = 0; n1 < 48; ++n1) v[n1] = w[n1];
+                }
+            }
+            if (kind == 0 || kind == 1 || kind == 2 || kind == 4 || kind == 6 || kind == 8 || kind == 10) __syncthreads();
+        }
+    }
+}
+
 // conv_fft_batch(H or conj(H), x), utils/utils_torch.py:46-50
 __global__ void __launch_bounds__(U_THREADS) k_conv_fft(const float* __restrict__ x, const float* __restrict__ psf,
                                                         float* __restrict__ out, int adjoint) {
@@ -781,6 +905,7 @@ int fft_kernels_init() {
     if ((rc = opt_in_smem(k_g_xupdate<true>, G_SMEM_XUP))) return rc;
     if ((rc = opt_in_smem(k_solver, SOLVER_SMEM))) return rc;
     if ((rc = opt_in_smem(k_wiener48, W48_SMEM))) return rc;
+    if ((rc = opt_in_smem(k_rl48, W48_SMEM))) return rc;
     if ((rc = opt_in_smem(k_conv_fft, SOLVER_SMEM))) return rc;
     if ((rc = opt_in_smem(k_psf_to_otf, SOLVER_SMEM_LIGHT))) return rc;
     if ((rc = opt_in_smem(k_conv_otf, SOLVER_SMEM_LIGHT))) return rc;
@@ -863,7 +988,7 @@ static int lap_table(float** out) {
     return GD_OK;
 }
 
-// GDECONV_SOLVER48=0 restores the phase-structured k_solver for Wiener / Tikhonov (Richardson-Lucy always runs in k_solver)
+// GDECONV_SOLVER48=0 restores the phase-structured k_solver for all classical solvers
 static int solver48_mode() {
     static int m = -1;
     if (m < 0) { const char* e = getenv("GDECONV_SOLVER48"); m = e ? atoi(e) : 1; }
@@ -873,6 +998,20 @@ static int solver48_mode() {
 int launch_solver(int kind, int n_iters, float lam, const float* y, const float* psf, const float* alpha, float* out,
                   int batch, cudaStream_t st) {
     if (batch <= 0) return GD_OK;
+    if (solver48_mode()) {
+        static int sms0 = 0;
+        if (!sms0) {
+            int dev;
+            GD_CUDA_CHECK(cudaGetDevice(&dev));
+            GD_CUDA_CHECK(cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const int groups0 = (batch + W48_G - 1) / W48_G;
+        if ((kind & 0xff) == 0) {
+            k_rl48<<<groups0 < 2 * sms0 ? groups0 : 2 * sms0, W48_THREADS, W48_SMEM, st>>>(n_iters, y, psf, out, batch);
+            GD_LAUNCHED();
+            return GD_OK;
+        }
+    }
     if ((kind & 0xff) != 0 && solver48_mode()) {
         float* lap = nullptr;
         if ((kind & 0xff) == 3) { int rc = lap_table(&lap); if (rc != GD_OK) return rc; }

@@ -80,6 +80,7 @@ import torch
 import oracle.ref_models as O
 from conftest import rel_l2
 from gdsynth import make_batch
+from models.Richard_Lucy import Richard_Lucy
 from models.Tikhonet import Tikhonov
 from models.Wiener import Wiener
 dev = torch.device('cuda:0')
@@ -88,6 +89,10 @@ for B in (1, 4, 5, 6, 1483):                      # below, at and above one CTA 
     b = make_batch(11, B, 'mixed', device=dev)
     idx = torch.arange(B) if B < 8 else torch.tensor([0, 4, 5, 741, 1479, 1480, 1482])
     args = [b[k][idx].cpu() for k in ('obs', 'psf', 'alpha')]
+    for n_it in ((0, 1, 3, 10) if B in (4, 6) else (10,)):
+        got = Richard_Lucy(n_it)(b['obs'], b['psf'])
+        res['rl'] = max(res.get('rl', 0.0), float(rel_l2(got[idx].cpu(), O.Richard_Lucy(n_it)(args[0], args[1])).max()))
+        res['finite'] = res.get('finite', True) and bool(torch.isfinite(got).all())
     for name, mine, ref in (('wiener', lambda: Wiener()(b['obs'], b['psf'], b['alpha']), lambda: O.Wiener()(*args)),
                             ('tik_id', lambda: Tikhonov('Identity')(b['obs'], b['psf'], b['alpha'], 0.7), lambda: O.Tikhonov('Identity')(*args, 0.7)),
                             ('tik_lap', lambda: Tikhonov('Laplacian')(b['obs'], b['psf'], b['alpha'], 1.3), lambda: O.Tikhonov('Laplacian')(*args, 1.3))):
@@ -100,11 +105,13 @@ print(json.dumps(res))
 
 @pytest.mark.parametrize('env', [{}, {'GDECONV_SOLVER48': '0'}], ids=['register-fft', 'phase-fft'])
 def test_wiener_tikhonov_kernels_match_reference(env):
-    """k_wiener48 (every 48-point transform in one thread's registers, five stamps per CTA pass) and the phase-structured k_solver it
-    replaces, on ragged batches, against the oracle (models/Wiener.py:10-20, models/Tikhonet.py:15-31); internal fp32 gate 2e-5"""
+    """k_wiener48 / k_rl48 (every 48-point transform in one thread's registers, five stamps per CTA pass) and the phase-structured
+    k_solver they replace, on ragged batches, against the oracle (models/Wiener.py:10-20, models/Tikhonet.py:15-31,
+    models/Richard_Lucy.py:10-24); internal fp32 gates 2e-5 / 2e-4"""
     r = subprocess.run([sys.executable, '-c', SOLVER_CHILD, ROOT], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
     assert res['finite']
     for k in ('wiener', 'tik_id', 'tik_lap'):
         assert res[k] < 2e-5, res
+    assert res['rl'] < 2e-4, res                  # Richardson-Lucy accumulates over its iterations: the internal gate of test_gpu_parity

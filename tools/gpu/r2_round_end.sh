@@ -30,6 +30,6 @@ full)
   ;;
 solver)
   timeout 600 python tools/gpu/solver_probe.py > gpurun_out/solver_probe.jsonl 2> gpurun_out/solver_probe.err; echo "probe rc=$?"; cat gpurun_out/solver_probe.jsonl
-  [ -s gpurun_out/solver_probe.jsonl ] && timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_solver|k_wiener48" -s 1 -c 1 -o gpurun_out/full_solver -f python tools/gpu/solver_probe.py > gpurun_out/ncu4.log 2>&1; echo "ncu solver rc=$?"
+  [ -s gpurun_out/solver_probe.jsonl ] && timeout 900 ncu --set full --import-source on --clock-control none -k regex:"${SOLVER_KERNEL:-k_wiener48}" -s 1 -c 1 -o gpurun_out/full_solver -f python tools/gpu/solver_probe.py > gpurun_out/ncu4.log 2>&1; echo "ncu solver rc=$?"
   ;;
 esac
