@@ -185,10 +185,17 @@ __global__ void __launch_bounds__(TAIL_ROWS) k_tail(const float* __restrict__ x3
 // 81-coefficient composite  tail(x1)[m] = sum_{tap2: m+off2 inside the stamp} sum_tap1 G[tap2][tap1] * t[m + off2 + off1],
 // G = W_tail W_head^T (kernel parameters), evaluated here from the padded-linear copy of t (zero halos) instead of 288 FMAs
 // per row in the conv epilogue.  `G == nullptr-like` (has_g = 0): P already contains x1.  Halo rows of P are never written.
-struct TailG { float g[81]; };
+// The zero padding of m_tail drops the taps t2 whose pixel lies outside the stamp, so the composite is one of NINE 5x5 stencils,
+// chosen by whether the pixel sits on the first / last row and column; the host collapses G (81 coefficients) into them.
+struct TailG { float g5[9 * 25]; };
 __global__ void __launch_bounds__(256) k_tail_gather(const float* __restrict__ P, int units, Geom g, const float* __restrict__ tscale,
                                                      float* __restrict__ z, int batch, const float* __restrict__ tpad, int has_g,
                                                      const __grid_constant__ TailG G, int t_plain) {
+    __shared__ float g5s[9 * 25];
+    if (has_g) {
+        if (threadIdx.x < 9 * 25) g5s[threadIdx.x] = G.g5[threadIdx.x];
+        __syncthreads();
+    }
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= batch * NPIX) return;
     const int b = idx / NPIX, r = idx - b * NPIX, y = r / STAMP, x = r - y * STAMP;
@@ -200,25 +207,22 @@ __global__ void __launch_bounds__(256) k_tail_gather(const float* __restrict__ P
         for (int t = 0; t < 9; ++t) s += __ldg(src + (size_t)(u * 9 + t) * g.Ptot + (t / 3 - 1) * g.Wp + (t % 3 - 1));
     }
     if (has_g) {
-        float tt[25];                             // 5x5 neighbourhood of t (zero outside the stamp)
+        // (a leaner address / predicate computation -- 118 M instead of 199 M warp instructions -- needs 75 registers and is SLOWER,
+        // 262 us against 234 us per 5000 stamps: the kernel is bound by bytes in flight, i.e. by resident threads)
+        const float* c5 = g5s + ((y == 0 ? 0 : y == STAMP - 1 ? 2 : 1) * 3 + (x == 0 ? 0 : x == STAMP - 1 ? 2 : 1)) * 25;
+        float a = 0.f;
 #pragma unroll
         for (int dy = -2; dy <= 2; ++dy)
 #pragma unroll
             for (int dx = -2; dx <= 2; ++dx) {
                 const int yy = y + dy, xx = x + dx;
-                // t_plain: `tpad` is the dense [B][48*48] denoiser input itself (conv_l1chain.cu path: no padded-linear copy exists)
-                tt[(dy + 2) * 5 + dx + 2] = (yy >= 0 && yy < STAMP && xx >= 0 && xx < STAMP)
-                                                ? (t_plain ? __ldg(tpad + (size_t)b * NPIX + yy * STAMP + xx) : __ldg(tpad + row + dy * g.Wp + dx)) : 0.f;
+                // 5x5 neighbourhood of t (zero outside the stamp).  t_plain: `tpad` is the dense [B][48*48] denoiser input itself
+                // (conv_l1chain.cu path: no padded-linear copy exists)
+                const float tv = (yy >= 0 && yy < STAMP && xx >= 0 && xx < STAMP)
+                                     ? (t_plain ? __ldg(tpad + (size_t)b * NPIX + yy * STAMP + xx) : __ldg(tpad + row + dy * g.Wp + dx)) : 0.f;
+                a = fmaf(c5[(dy + 2) * 5 + dx + 2], tv, a);
             }
-#pragma unroll
-        for (int t2 = 0; t2 < 9; ++t2) {
-            const int y2 = y + t2 / 3 - 1, x2 = x + t2 % 3 - 1;
-            if (y2 < 0 || y2 >= STAMP || x2 < 0 || x2 >= STAMP) continue;      // m_tail zero-pads x + x1
-            float a = 0.f;
-#pragma unroll
-            for (int t1 = 0; t1 < 9; ++t1) a = fmaf(G.g[t2 * 9 + t1], tt[(t2 / 3 + t1 / 3) * 5 + (t2 % 3 + t1 % 3)], a);
-            s += a;
-        }
+        s += a;
     }
     z[idx] = s * tscale[b];
 }
@@ -254,7 +258,20 @@ int launch_tail_gather(const float* P, int units, const Geom& g, const float* ts
     if (batch <= 0) return GD_OK;
     TailG G;
     memset(&G, 0, sizeof(G));
-    if (G81_host) memcpy(G.g, G81_host, sizeof(G.g));
+    if (G81_host) {
+        // G81[t2 * 9 + t1]: tail tap t2 (pixel p + t2) times head tap t1 (input p + t2 + t1).  Class (cy, cx): 0 = first row / column
+        // (tap -1 falls outside and is dropped), 2 = last, 1 = interior.
+        double acc[9 * 25] = {0};
+        for (int cy = 0; cy < 3; ++cy)
+            for (int cx = 0; cx < 3; ++cx)
+                for (int t2 = 0; t2 < 9; ++t2) {
+                    const int ty = t2 / 3, tx = t2 % 3;
+                    if ((cy == 0 && ty == 0) || (cy == 2 && ty == 2) || (cx == 0 && tx == 0) || (cx == 2 && tx == 2)) continue;
+                    for (int t1 = 0; t1 < 9; ++t1)
+                        acc[(cy * 3 + cx) * 25 + (ty + t1 / 3) * 5 + (tx + t1 % 3)] += (double)G81_host[t2 * 9 + t1];
+                }
+        for (int i = 0; i < 9 * 25; ++i) G.g5[i] = (float)acc[i];
+    }
     k_tail_gather<<<(batch * NPIX + 255) / 256, 256, 0, st>>>(P, units, g, tscale, z, batch, tpad, G81_host != nullptr, G, t_plain);
     GD_LAUNCHED();
     return GD_OK;
