@@ -622,8 +622,9 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         }
         if (L == 1 && l2chain) {
             const void* w4[4] = {W->down_rb[1][0][0], W->down_rb[1][0][1], W->down_rb[1][1][0], W->down_rb[1][1][1]};
-            Geom g2 = g[2]; g2.M = n * g[2].S;
-            GD_TRY(launch_l2chain(0, g[1], g2, n, at(ws.a16[1], 1, s0), at(ws.lo16[1], 1, s0), w4, at(ws.d16[2], 2, s0), nullptr, nullptr, st));
+            // ... and the k2s2 strided conv of m_down2 (its space-to-depth operand never leaves shared memory)
+            return launch_l2chain(0, g[1], g[2], n, at(ws.a16[1], 1, s0), at(ws.lo16[1], 1, s0), w4, W->down[1], (float*)at(ws.skip32[2], 2, s0),
+                                  at(ws.a16[2], 2, s0), nullptr, nullptr, st);
         } else
             GD_TRY(resblock_pair(L, s0, n, W->down_rb[L][0], W->down_rb[L][1], ws.skip32[L], ws.p32a[L], ws.a16[L], ws.p32a[L], nullptr,
                                  nullptr, nullptr, ws.d16[L + 1]));
@@ -645,8 +646,8 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
         GD_TRY(run_conv(p, prec, st));
         if (L == 1 && l2chain) {
             const void* w4[4] = {W->up_rb[1][0][0], W->up_rb[1][0][1], W->up_rb[1][1][0], W->up_rb[1][1][1]};
-            return launch_l2chain(1, g[1], g[2], n, at(ws.a16[1], 1, s0), at(ws.lo16[1], 1, s0), w4, nullptr, (const float*)at(ws.skip32[1], 1, s0),
-                                  at(ws.a16[1], 1, s0), st);
+            return launch_l2chain(1, g[1], g[2], n, at(ws.a16[1], 1, s0), at(ws.lo16[1], 1, s0), w4, nullptr, nullptr, nullptr,
+                                  (const float*)at(ws.skip32[1], 1, s0), at(ws.a16[1], 1, s0), st);
         }
         if (L > 0) return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L],
                                         ws.skip32[L], nullptr, ws.a16[L], nullptr);

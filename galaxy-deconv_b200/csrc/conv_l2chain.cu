@@ -54,7 +54,13 @@ constexpr int L2_EPI_GROUPS = 3;                     // warps 4-15: three groups
 constexpr int L2_LAG = 4;                            // phase 1 runs this many taps behind phase 0 on the same ring of tap slices
 constexpr int L2_X0_ROWS = (L2_PH0_TILES + 1) * MTILE;          // 384: rows of tiles 0..2, everything phase 0 reads
 
-enum { L2B_X_FULL = 0, L2B_T_FULL = 2, L2B_T_FREE, L2B_LO_DONE, L2B_ACC_FULL, L2B_TILE_DONE = L2B_ACC_FULL + 2, L2B_W_FULL = L2B_TILE_DONE + L2_TILES,
+// m_down2's k2s2 strided conv (64 -> 128 channels, 12x12) on the space-to-depth operand the last epilogue leaves in the T planes
+constexpr int L2_DS = 169;                           // rows of one coarse stamp = rows per K chunk of the operand [32][169][8]
+constexpr int L2_DN = 128;                           // its output channels
+constexpr int L2_DSTAGES = 32 * L2_DN * 16 / L2_WSTAGE;         // 8 ring stages of two K16 steps each
+static_assert(32 * L2_DS * 16 == (8 * L2_PSTRIDE + L2_GAP) * 16, "the operand fills the T planes and the trailing gap exactly");
+
+enum { L2B_X_FULL = 0, L2B_DOWN_FULL = 2, L2B_DOWN_EMPTY, L2B_MMA_DONE, L2B_LO_DONE, L2B_ACC_FULL, L2B_TILE_DONE = L2B_ACC_FULL + 2, L2B_W_FULL = L2B_TILE_DONE + L2_TILES,
        L2B_W_EMPTY = L2B_W_FULL + L2_WSTAGES, L2B_COUNT = L2B_W_EMPTY + L2_WSTAGES };
 
 struct L2ChainParams {
@@ -62,7 +68,9 @@ struct L2ChainParams {
     Geom g1, g2;                   // 24x24 and 12x12 geometry of the chunk
     const void *x_hi, *x_lo;       // fp16 hi / lo planes of the stage's input stream [8][g1.Ptot][8]
     const void* w[4];              // packed 3x3 weights [tap][8][64][8]
-    void* s2d;                     // mode 0: space-to-depth copy [32][g2.Ptot][8] for the strided conv
+    const void* wdown;             // mode 0: strided-conv weights [32][128][8]
+    float* skip3;                  // mode 0: x3 fp32 [32][g2.Ptot][4] (U-Net skip + residual of level 2)
+    void* x3_16;                   // mode 0: x3 fp16 [16][g2.Ptot][8] (operand of level 2's first conv)
     const float* skip32;           // mode 1: U-Net skip x2, fp32 [16][g1.Ptot][4]
     void* out16;                   // mode 1: fp16 (x + x2) [8][g1.Ptot][8] (input of m_up1's transposed conv)
 };
@@ -78,7 +86,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
     if (threadIdx.x == 0) {
-        mbar_init(bar(L2B_X_FULL), 1); mbar_init(bar(L2B_X_FULL + 1), 1); mbar_init(bar(L2B_T_FULL), 1); mbar_init(bar(L2B_T_FREE), 3); mbar_init(bar(L2B_LO_DONE), 4);
+        mbar_init(bar(L2B_X_FULL), 1); mbar_init(bar(L2B_X_FULL + 1), 1); mbar_init(bar(L2B_DOWN_FULL), 3); mbar_init(bar(L2B_DOWN_EMPTY), 12); mbar_init(bar(L2B_MMA_DONE), 3); mbar_init(bar(L2B_LO_DONE), 4);
         mbar_init(bar(L2B_ACC_FULL), 3); mbar_init(bar(L2B_ACC_FULL + 1), 3);
         for (int t = 0; t < L2_TILES; ++t) mbar_init(bar(L2B_TILE_DONE + t), 8);          // 2 channel halves x 4 quadrant warps
         for (int s = 0; s < L2_WSTAGES; ++s) { mbar_init(bar(L2B_W_FULL + s), 1); mbar_init(bar(L2B_W_EMPTY + s), 3); }
@@ -109,15 +117,19 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
         // ===== producers: lane 0 streams the tap slices, lane 1 the activation planes (independent waits) =====
         if (lane == 0) {
             uint32_t wc = 0;                              // running weight-stage counter
-            for (int k = 0; k < n_my; ++k)
+            auto stage = [&](const void* src) {
+                const uint32_t s = wc % L2_WSTAGES;
+                mbar_wait(bar(L2B_W_EMPTY + s), ((wc / L2_WSTAGES) & 1) ^ 1);
+                mbar_expect_tx(bar(L2B_W_FULL + s), (uint32_t)L2_WSTAGE);
+                bulk_g2s(smem_u32(w_smem) + s * L2_WSTAGE, src, (uint32_t)L2_WSTAGE, bar(L2B_W_FULL + s));
+                ++wc;
+            };
+            for (int k = 0; k < n_my; ++k) {
                 for (int c = 0; c < 4; ++c)
-                    for (int tap = 0; tap < 9; ++tap, ++wc) {
-                        const uint32_t s = wc % L2_WSTAGES;
-                        mbar_wait(bar(L2B_W_EMPTY + s), ((wc / L2_WSTAGES) & 1) ^ 1);
-                        mbar_expect_tx(bar(L2B_W_FULL + s), (uint32_t)L2_WSTAGE);
-                        bulk_g2s(smem_u32(w_smem) + s * L2_WSTAGE, reinterpret_cast<const unsigned char*>(p.w[c]) + (size_t)tap * L2_WSTAGE,
-                                 (uint32_t)L2_WSTAGE, bar(L2B_W_FULL + s));
-                    }
+                    for (int tap = 0; tap < 9; ++tap) stage(reinterpret_cast<const unsigned char*>(p.w[c]) + (size_t)tap * L2_WSTAGE);
+                if (MODE == 0)
+                    for (int i = 0; i < L2_DSTAGES; ++i) stage(reinterpret_cast<const unsigned char*>(p.wdown) + (size_t)i * L2_WSTAGE);
+            }
         } else if (lane == 1) {
             auto plane_src = [&](const void* src, int ch, int b) {
                 return reinterpret_cast<const unsigned char*>(src) + ((size_t)ch * Ptot1 + (size_t)p.g1.base0 + (size_t)b * p.g1.S) * 16;
@@ -130,8 +142,9 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
             };
             for (int k = 0; k < n_my; ++k) {
                 const int b = (int)blockIdx.x + k * (int)gridDim.x;
-                mbar_wait(bar(L2B_T_FREE), (uint32_t)((k & 1) ^ 1));          // the previous item's conv 3 has finished reading T
-                load_planes(b, p.x_lo, 8, 0, L2_S, bar(L2B_T_FULL));
+                // once per item: the previous item's last conv has been issued and completed, so every tile barrier has passed its
+                // completion 4k - 2 and the parity waits below cannot alias an older phase (this lane is not tied to the weight ring)
+                mbar_wait(bar(L2B_MMA_DONE), (uint32_t)((k & 1) ^ 1));
                 // X in two parts, each as soon as the previous item's last epilogues (n = 4k - 1) have read their residual hi from it
                 wait_tiles(0, L2_PH0_TILES, 4 * k - 1);
                 load_planes(b, p.x_hi, 0, 0, L2_X0_ROWS, bar(L2B_X_FULL));
@@ -171,7 +184,10 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
                 };
                 // input rows written back (tile t reads the rows of tiles t-1 .. t+1) and accumulators drained: tiles 0..2 for phase 0
                 wait_tiles(0, L2_PH0_TILES, n - 1);
-                if (c == 0) mbar_wait(bar(L2B_X_FULL), (uint32_t)(k & 1));
+                if (c == 0) {
+                    mbar_wait(bar(L2B_X_FULL), (uint32_t)(k & 1));
+                    if (MODE == 0) mbar_wait(bar(L2B_DOWN_EMPTY), (uint32_t)((k & 1) ^ 1));    // the previous item's strided-conv accumulators are drained
+                }
                 tc_fence_after();
                 constexpr int LAG = L2_LAG;
                 for (int i = 0; i < 9 + LAG; ++i) {
@@ -198,9 +214,39 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
                 }
                 if (elect_one()) {
                     tc_commit(bar(L2B_ACC_FULL + 1));
-                    if (c == 3) tc_commit(bar(L2B_T_FREE));
+                    if (c == 3) tc_commit(bar(L2B_MMA_DONE));
                 }
                 __syncwarp();
+            }
+            if (MODE == 0) {
+                // ---- m_down2's strided conv: two M128 N128 tiles (coarse rows 0..255, 156 of them real), K = 256 in 16 steps ----
+                wait_tiles(0, L2_TILES - 1, 4 * k + 3);           // the operand is complete and the conv accumulators are drained
+                tc_fence_after();
+                const uint32_t idesc_d = instr_desc_f16(MTILE, L2_DN);
+                const uint64_t ad0 = smem_desc(smem_u32(smem) + 8 * L2_PSTRIDE * 16, L2_DS * 16, 128) + (uint64_t)(uint32_t)(jw * MTILE);
+                const uint64_t wd0 = smem_desc(smem_u32(w_smem), L2_DN * 16, 128);
+                for (int i = 0; i < L2_DSTAGES; ++i) {
+                    const uint32_t w = wc0 + (uint32_t)i, st = w % L2_WSTAGES;
+                    mbar_wait(bar(L2B_W_FULL + st), (w / L2_WSTAGES) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        if (jw < 2) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int kk = 2 * i + h;
+                                const uint64_t ad = ad0 + (uint64_t)(uint32_t)(kk * 2 * L2_DS);
+                                const uint64_t wd = wd0 + (uint64_t)(st * (L2_WSTAGE >> 4) + h * (L2_WSTAGE >> 5));
+                                if (kk == 0) tc_mma_f16(tmem + (uint32_t)(jw * L2_DN), ad, wd, idesc_d, 0u);
+                                else tc_mma_f16_acc(tmem + (uint32_t)(jw * L2_DN), ad, wd, idesc_d);
+                            }
+                        }
+                        tc_commit(bar(L2B_W_EMPTY + st));
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) tc_commit(bar(L2B_DOWN_FULL));
+                __syncwarp();
+                wc0 += L2_DSTAGES;
             }
         }
     } else {
@@ -211,15 +257,28 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
         for (int k = 0; k < n_my; ++k) {
             const int b = (int)blockIdx.x + k * (int)gridDim.x;
             if (warp < 8) {
-                mbar_wait(bar(L2B_T_FULL), (uint32_t)(k & 1));
+                if (MODE == 0 && k > 0) {
+                    // the strided conv's operand overwrote ALL of T: restore the never-written zero rows (gap above each plane, pad column,
+                    // zero rows below the stamp) before this item's conv 1 reads T; the valid rows are rewritten by conv 0's epilogue
+                    for (int i = (warp - 4) * 32 + lane; i < 8 * 96 + L2_GAP; i += 128) {
+                        int pl, s;
+                        if (i < 8 * 96) {
+                            const int j = i % 96;
+                            pl = 8 + i / 96;
+                            s = j < 32 ? j - 32 : j < 56 ? 25 * (j - 32) + 24 : 600 + (j - 56);
+                        } else { pl = 15; s = 640 + (i - 8 * 96); }
+                        *reinterpret_cast<uint4*>(smem + row_off(pl, s)) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
                 wait_tiles(0, L2_TILES - 1, 4 * k - 1);                      // the previous item's last epilogues have read the lo stream
                 tc_fence_after();
+                const uint4* lo_g = reinterpret_cast<const uint4*>(p.x_lo) + (size_t)p.g1.base0 + (size_t)b * p.g1.S;
                 for (int t = 0; t < L2_TILES; ++t) {
                     const int s = t * MTILE + q * 32 + lane;
                     uint4 lo[8];
 #pragma unroll
                     for (int ch = 0; ch < 8; ++ch)
-                        lo[ch] = s < L2_S ? *reinterpret_cast<const uint4*>(smem + row_off(8 + ch, s)) : make_uint4(0u, 0u, 0u, 0u);
+                        lo[ch] = s < L2_S ? __ldg(lo_g + (size_t)ch * Ptot1 + s) : make_uint4(0u, 0u, 0u, 0u);
                     const uint32_t taddr = tmem + lane_base + (uint32_t)(L2_LO_COL + t * 32);
                     tc_st16(taddr, reinterpret_cast<const uint32_t*>(lo));
                     tc_st16(taddr + 16, reinterpret_cast<const uint32_t*>(lo) + 16);
@@ -237,7 +296,9 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
                     if (ph != ph_waited) {
                         if (ph_waited < 0 && ph == 1) mbar_wait(bar(L2B_ACC_FULL), (uint32_t)(n & 1));     // keep every barrier at most one phase ahead
                         mbar_wait(bar(L2B_ACC_FULL + ph), (uint32_t)(n & 1));
-                        if (c == 0 && ph_waited < 0) mbar_wait(bar(L2B_LO_DONE), (uint32_t)(k & 1));   // T no longer holds the lo halves
+                        // DOWN, last conv: its epilogue writes the strided conv's operand over T, which the MMAs of phase 1 still read
+                        if (MODE == 0 && c == 3 && ph == 0) mbar_wait(bar(L2B_ACC_FULL + 1), (uint32_t)(n & 1));
+                        if (c == 1 && ph_waited < 0) mbar_wait(bar(L2B_LO_DONE), (uint32_t)(k & 1));   // the lo halves of the input stream are in tensor memory
                         tc_fence_after();
                         ph_waited = ph;
                     }
@@ -285,12 +346,12 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
                             tc_st_wait();
                         } else if (valid) {
                             if (MODE == 0) {
-                                // space-to-depth copy for m_down2's strided conv: K chunk = (dy*2+dx)*8 + channel chunk, coarse row of g2
-                                const Geom& g2 = p.g2;
-                                const int crow = g2.base0 + b * g2.S + (y >> 1) * g2.Wp + (x >> 1), ctap = ((y & 1) << 1) | (x & 1);
-                                uint4* dst = reinterpret_cast<uint4*>(p.s2d) + (size_t)(ctap * 8 + 4 * hf) * g2.Ptot + crow;
+                                // space-to-depth operand of m_down2's strided conv, [32][169][8] over the T planes: K chunk =
+                                // (dy*2+dx)*8 + channel chunk, row = coarse padded-linear row
+                                const int crow = (y >> 1) * 13 + (x >> 1), ctap = ((y & 1) << 1) | (x & 1);
+                                uint4* dst = reinterpret_cast<uint4*>(smem + 8 * L2_PSTRIDE * 16) + (ctap * 8 + 4 * hf) * L2_DS + crow;
 #pragma unroll
-                                for (int ch = 0; ch < 4; ++ch) dst[(size_t)ch * g2.Ptot] = pack8_half(v + 8 * ch);
+                                for (int ch = 0; ch < 4; ++ch) dst[ch * L2_DS] = pack8_half(v + 8 * ch);
                             } else {
                                 const size_t row = (size_t)p.g1.base0 + (size_t)b * p.g1.S + (size_t)s;
                                 const float4* sk = reinterpret_cast<const float4*>(p.skip32) + (size_t)(8 * hf) * Ptot1 + row;
@@ -313,6 +374,35 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
                 // a group whose units all lie in phase 0 or all in phase 1 still has to follow both accumulator barriers
                 if (ph_waited == 0) mbar_wait(bar(L2B_ACC_FULL + 1), (uint32_t)(n & 1));
             }
+            if (MODE == 0) {
+                // ---- strided-conv epilogue: unit = (tile, 32-channel quarter), eight units round robin over the three groups ----
+                mbar_wait(bar(L2B_DOWN_FULL), (uint32_t)(k & 1));
+                tc_fence_after();
+                const Geom& g2 = p.g2;
+                for (int u = grp; u < 8; u += L2_EPI_GROUPS) {
+                    const int j = u >> 2, qq = u & 3;
+                    const uint32_t a = tmem + lane_base + (uint32_t)(j * L2_DN + qq * 32);
+                    uint32_t d0[16], d1[16];
+                    tc_ld16_nowait(a, d0); tc_ld16_nowait(a + 16, d1);
+                    const int cr = j * MTILE + q * 32 + lane, cy = (cr * 5042) >> 16, cx = cr - cy * 13;        // cr / 13 exactly for cr < 256
+                    tc_ld_wait16(d0); tc_ld_wait16(d1);
+                    if (cr < 156 && cx < 12) {
+                        const size_t row = (size_t)g2.base0 + (size_t)b * g2.S + (size_t)cr;
+                        float4* o32 = reinterpret_cast<float4*>(p.skip3) + (size_t)(qq * 8) * g2.Ptot + row;
+                        uint4* o16 = reinterpret_cast<uint4*>(p.x3_16) + (size_t)(qq * 4) * g2.Ptot + row;
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(d0[i]); v[16 + i] = __uint_as_float(d1[i]); }
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) o32[(size_t)c4 * g2.Ptot] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8) o16[(size_t)c8 * g2.Ptot] = pack8_half(v + 8 * c8);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(L2B_DOWN_EMPTY));
+            }
         }
     }
     tc_fence_before();
@@ -334,21 +424,21 @@ int conv_l2chain_init() {
     return GD_OK;
 }
 
-int launch_l2chain(int mode, const Geom& g1, const Geom& g2, int nb, const void* x_hi, const void* x_lo, const void* const* w4, void* s2d,
-                   const float* skip32, void* out16, cudaStream_t st) {
+int launch_l2chain(int mode, const Geom& g1, const Geom& g2, int nb, const void* x_hi, const void* x_lo, const void* const* w4, const void* wdown,
+                   float* skip3, void* x3_16, const float* skip32, void* out16, cudaStream_t st) {
     if (nb <= 0) return GD_OK;
     if (!g_l2_sms) { set_error("conv_l2chain: library not initialised"); return GD_ECUDA; }
-    if (g1.Wp != L2_WP || g1.S != L2_S || g2.Wp != 13) { set_error("conv_l2chain: needs the 24x24 / 12x12 geometries"); return GD_EUNSUPPORTED; }
+    if (g1.Wp != L2_WP || g1.S != L2_S || g2.Wp != 13 || g2.S != L2_DS) { set_error("conv_l2chain: needs the 24x24 / 12x12 geometries"); return GD_EUNSUPPORTED; }
     L2ChainParams p;
     memset(&p, 0, sizeof(p));
-    p.nb = nb; p.mode = mode; p.g1 = g1; p.g2 = g2; p.x_hi = x_hi; p.x_lo = x_lo; p.s2d = s2d; p.skip32 = skip32; p.out16 = out16;
+    p.nb = nb; p.mode = mode; p.g1 = g1; p.g2 = g2; p.x_hi = x_hi; p.x_lo = x_lo; p.wdown = wdown; p.skip3 = skip3; p.x3_16 = x3_16; p.skip32 = skip32; p.out16 = out16;
     for (int i = 0; i < 4; ++i) p.w[i] = w4[i];
-    if (!x_hi || !x_lo || !w4[0] || !w4[1] || !w4[2] || !w4[3] || (mode == 0 ? !s2d : (!skip32 || !out16))) {
+    if (!x_hi || !x_lo || !w4[0] || !w4[1] || !w4[2] || !w4[3] || (mode == 0 ? (!wdown || !skip3 || !x3_16) : (!skip32 || !out16))) {
         set_error("conv_l2chain: missing buffer"); return GD_EBADSHAPE;
     }
     const int grid = nb < g_l2_sms ? nb : g_l2_sms;
     cudaEvent_t e1 = nullptr;
-    const double flops = 4.0 * 2.0 * (double)nb * 576 * (double)L2_C * L2_C * 9;
+    const double flops = 4.0 * 2.0 * (double)nb * 576 * (double)L2_C * L2_C * 9 + (mode == 0 ? 2.0 * (double)nb * 144 * 256 * L2_DN : 0.0);
     { int rc = conv_profile_mark(flops, st, &e1); if (rc != GD_OK) return rc; }
     if (mode == 0) k_l2_chain<0><<<grid, L2_THREADS, L2_SMEM, st>>>(p);
     else k_l2_chain<1><<<grid, L2_THREADS, L2_SMEM, st>>>(p);
