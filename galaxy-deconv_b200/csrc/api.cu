@@ -61,6 +61,7 @@ struct GdWeights {
     const void* body_rb[2][2];
     const void* up[3];                // k2s2 transposed conv C_{L+1} -> C_L (index = fine level L)
     const void* up_rb[3][2][2];
+    const void* up1_plain;            // C1 = 64: m_up2's transposed conv in the same plain order (conv_l2chain.cu)
     const void* up0_plain;            // C0 = 32, tcgen05 path: m_up1's transposed conv with plain column order n = (dy*2+dx)*C0 + co (conv_l1chain.cu)
     gd::SubnetParams sub;
     const float* rho_param;           // [n_rho] when subnet=False
@@ -261,6 +262,7 @@ extern "C" int gd_pack_weights(int arch, int n_iters, const GdTensorDesc* tensor
             GD_TRY(pack_up(bl, F.net(key), 2 * C, C, precision, &off, key));
             slot(&W.up[L], off);
             if (L == 0 && C == 32 && precision == PREC_FP16_UMMA) { GD_TRY(pack_up_plain(bl, F.net(key), 2 * C, C, &off, key)); slot(&W.up0_plain, off); }
+            if (L == 1 && C == 64 && precision == PREC_FP16_UMMA) { GD_TRY(pack_up_plain(bl, F.net(key), 2 * C, C, &off, key)); slot(&W.up1_plain, off); }
         }
         for (int blk = 0; blk < 2; ++blk)
             for (int j = 0; j < 2; ++j) {
@@ -404,7 +406,7 @@ static Ws ws_layout(unsigned char* base, int arch, int prec, int chunk) {
         w.lo16[L] = take(n * es);
         if (L > 0) w.d16[L] = take((size_t)2 * n * es);        // 4*C_{L-1} = 2*C_L channels
     }
-    w.lc_scratch = C0 == 32 ? take(l1chain_scratch_bytes()) : nullptr;
+    w.lc_scratch = C0 == 32 ? take(l1chain_scratch_bytes() > l2chain_scratch_bytes() ? l1chain_scratch_bytes() : l2chain_scratch_bytes()) : nullptr;
     w.tpad = (float*)take((size_t)w.g[0].Ptot * 4);
     w.tail_part = (float*)take((size_t)(C0 / 16) * 9 * w.g[0].Ptot * 4);   // 32-channel units (conv_umma.cu) or 16-channel halves (conv_rb.cu)
     w.total = off;
@@ -526,7 +528,7 @@ static int l2chain_mode() {
     return g_l2chain;
 }
 static bool l2chain_applies(const GdWeights* W) {
-    return l2chain_mode() && l1chain_applies(W) && W->nc[1] == 64;
+    return l2chain_mode() && l1chain_applies(W) && W->nc[1] == 64 && W->up1_plain;
 }
 static bool xhead_applies(const GdWeights* W) {
     return xhead_mode() && W->precision == PREC_FP16_UMMA && W->nc[0] == 32 && g_fuse_ht_fwd() && !l1chain_applies(W);
@@ -624,7 +626,7 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
             const void* w4[4] = {W->down_rb[1][0][0], W->down_rb[1][0][1], W->down_rb[1][1][0], W->down_rb[1][1][1]};
             // ... and the k2s2 strided conv of m_down2 (its space-to-depth operand never leaves shared memory)
             return launch_l2chain(0, g[1], g[2], n, at(ws.a16[1], 1, s0), at(ws.lo16[1], 1, s0), w4, W->down[1], (float*)at(ws.skip32[2], 2, s0),
-                                  at(ws.a16[2], 2, s0), nullptr, nullptr, st);
+                                  at(ws.a16[2], 2, s0), nullptr, nullptr, nullptr, nullptr, nullptr, st);
         } else
             GD_TRY(resblock_pair(L, s0, n, W->down_rb[L][0], W->down_rb[L][1], ws.skip32[L], ws.p32a[L], ws.a16[L], ws.p32a[L], nullptr,
                                  nullptr, nullptr, ws.d16[L + 1]));
@@ -638,17 +640,17 @@ static int resunet_chunk(const GdWeights* W, const Ws& ws, const float* t, const
             const void* w4[4] = {W->up_rb[0][0][0], W->up_rb[0][0][1], W->up_rb[0][1][0], W->up_rb[0][1][1]};
             return launch_l1chain_up(g[0], g[1], n, at(ws.a16[1], 1, s0), W->up0_plain, W->tail_h, w4, at4(ws.tail_part, s0), ws.lc_scratch, st);
         }
+        if (L == 1 && l2chain) {          // transposed conv + both ResBlocks + U-Net skip in one launch
+            const void* w4[4] = {W->up_rb[1][0][0], W->up_rb[1][0][1], W->up_rb[1][1][0], W->up_rb[1][1][1]};
+            return launch_l2chain(1, g[1], g[2], n, nullptr, nullptr, w4, nullptr, nullptr, nullptr, at(ws.a16[2], 2, s0), W->up1_plain, ws.lc_scratch,
+                                  (const float*)at(ws.skip32[1], 1, s0), at(ws.a16[1], 1, s0), st);
+        }
         ConvParams p = conv_base(g[L + 1], n);         // k2s2 transposed conv: GEMM on the coarse level, scatter to fine
         p.ntaps = 1; p.off[0] = 0; p.Kt = C[L + 1]; p.N = 4 * C[L]; p.a = at(ws.a16[L + 1], L + 1, s0); p.w = W->up[L];
         p.mode = 1; p.Cf = C[L]; p.Cf_log2 = 0; while ((1 << p.Cf_log2) < p.Cf) ++p.Cf_log2; p.gf = g[L]; p.gf.M = n * g[L].S;
         p.out32 = (float*)at(ws.p32a[L], L, s0); p.out16 = at(ws.a16[L], L, s0);
         if (hilo) { p.out_lo = at(ws.lo16[L], L, s0); p.out32 = nullptr; }
         GD_TRY(run_conv(p, prec, st));
-        if (L == 1 && l2chain) {
-            const void* w4[4] = {W->up_rb[1][0][0], W->up_rb[1][0][1], W->up_rb[1][1][0], W->up_rb[1][1][1]};
-            return launch_l2chain(1, g[1], g[2], n, at(ws.a16[1], 1, s0), at(ws.lo16[1], 1, s0), w4, nullptr, nullptr, nullptr,
-                                  (const float*)at(ws.skip32[1], 1, s0), at(ws.a16[1], 1, s0), st);
-        }
         if (L > 0) return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L],
                                         ws.skip32[L], nullptr, ws.a16[L], nullptr);
         return resblock_pair(L, s0, n, W->up_rb[L][0], W->up_rb[L][1], ws.p32a[L], ws.p32b[L], ws.a16[L], ws.p32b[L], ws.skip32[L],

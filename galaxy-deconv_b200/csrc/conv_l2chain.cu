@@ -60,6 +60,12 @@ constexpr int L2_DN = 128;                           // its output channels
 constexpr int L2_DSTAGES = 32 * L2_DN * 16 / L2_WSTAGE;         // 8 ring stages of two K16 steps each
 static_assert(32 * L2_DS * 16 == (8 * L2_PSTRIDE + L2_GAP) * 16, "the operand fills the T planes and the trailing gap exactly");
 
+// m_up2's k2s2 transposed conv (128 -> 4 x 64 channels) at the head of an UP item: A = the coarse fp16 map [16][169][8] in the T planes,
+// N = 256 (column = sub-pixel * 64 + channel), two M128 tiles over all 512 TMEM columns
+constexpr int L2_UN = 256;
+constexpr int L2_USTAGES = 16 * L2_UN * 16 / L2_WSTAGE;         // 8 ring stages, one K16 step each
+constexpr int L2_SCRATCH_BYTES = 8 * L2_S * 16;                 // per CTA: lo halves of the transposed conv's output, [8][625][8] fp16
+
 enum { L2B_X_FULL = 0, L2B_DOWN_FULL = 2, L2B_DOWN_EMPTY, L2B_MMA_DONE, L2B_LO_DONE, L2B_ACC_FULL, L2B_TILE_DONE = L2B_ACC_FULL + 2, L2B_W_FULL = L2B_TILE_DONE + L2_TILES,
        L2B_W_EMPTY = L2B_W_FULL + L2_WSTAGES, L2B_COUNT = L2B_W_EMPTY + L2_WSTAGES };
 
@@ -68,6 +74,8 @@ struct L2ChainParams {
     Geom g1, g2;                   // 24x24 and 12x12 geometry of the chunk
     const void *x_hi, *x_lo;       // fp16 hi / lo planes of the stage's input stream [8][g1.Ptot][8]
     const void* w[4];              // packed 3x3 weights [tap][8][64][8]
+    const void *a_coarse, *wup;    // mode 1: fp16 input of m_up2's transposed conv [16][g2.Ptot][8], its weights [16][256][8] (plain column order)
+    void* scratch;                 // mode 1: L2_SCRATCH_BYTES per CTA
     const void* wdown;             // mode 0: strided-conv weights [32][128][8]
     float* skip3;                  // mode 0: x3 fp32 [32][g2.Ptot][4] (U-Net skip + residual of level 2)
     void* x3_16;                   // mode 0: x3 fp16 [16][g2.Ptot][8] (operand of level 2's first conv)
@@ -125,6 +133,8 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
                 ++wc;
             };
             for (int k = 0; k < n_my; ++k) {
+                if (MODE == 1)
+                    for (int i = 0; i < L2_USTAGES; ++i) stage(reinterpret_cast<const unsigned char*>(p.wup) + (size_t)i * L2_WSTAGE);
                 for (int c = 0; c < 4; ++c)
                     for (int tap = 0; tap < 9; ++tap) stage(reinterpret_cast<const unsigned char*>(p.w[c]) + (size_t)tap * L2_WSTAGE);
                 if (MODE == 0)
@@ -145,17 +155,28 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
                 // once per item: the previous item's last conv has been issued and completed, so every tile barrier has passed its
                 // completion 4k - 2 and the parity waits below cannot alias an older phase (this lane is not tied to the weight ring)
                 mbar_wait(bar(L2B_MMA_DONE), (uint32_t)((k & 1) ^ 1));
+                if (MODE == 1) {
+                    // the coarse map of the transposed conv -> T (conv 3 of the previous item has finished reading it: MMA_DONE)
+                    auto coarse_src = [&](int ch, int bb) {
+                        return reinterpret_cast<const unsigned char*>(p.a_coarse) + ((size_t)ch * p.g2.Ptot + (size_t)p.g2.base0 + (size_t)bb * L2_DS) * 16;
+                    };
+                    mbar_expect_tx(bar(L2B_X_FULL), 16u * L2_DS * 16u);
+                    for (int ch = 0; ch < 16; ++ch)
+                        bulk_g2s(smem_u32(smem) + (uint32_t)((8 * L2_PSTRIDE + ch * L2_DS) * 16), coarse_src(ch, b), (uint32_t)L2_DS * 16u, bar(L2B_X_FULL));
+                    if (k + 1 < n_my)
+                        for (int ch = 0; ch < 16; ++ch) bulk_prefetch_l2(coarse_src(ch, b + (int)gridDim.x), L2_DS * 16u);
+                    for (int ch = 0; ch < 16; ++ch) bulk_prefetch_l2(plane_src(p.skip32, ch, b), L2_S * 16u);
+                    continue;
+                }
                 // X in two parts, each as soon as the previous item's last epilogues (n = 4k - 1) have read their residual hi from it
                 wait_tiles(0, L2_PH0_TILES, 4 * k - 1);
                 load_planes(b, p.x_hi, 0, 0, L2_X0_ROWS, bar(L2B_X_FULL));
                 wait_tiles(L2_PH0_TILES + 1, L2_TILES - 1, 4 * k - 1);
                 load_planes(b, p.x_hi, 0, L2_X0_ROWS, L2_S, bar(L2B_X_FULL + 1));
-                if (k + 1 < n_my) {                       // the next item's planes (and this item's skip) on their way into L2
+                if (k + 1 < n_my) {                       // the next item's planes on their way into L2
                     const int bn = b + (int)gridDim.x;
                     for (int ch = 0; ch < 8; ++ch) { bulk_prefetch_l2(plane_src(p.x_hi, ch, bn), L2_S * 16u); bulk_prefetch_l2(plane_src(p.x_lo, ch, bn), L2_S * 16u); }
                 }
-                if (MODE == 1)
-                    for (int ch = 0; ch < 16; ++ch) bulk_prefetch_l2(plane_src(p.skip32, ch, b), L2_S * 16u);
             }
         }
     } else if (warp <= 3) {
@@ -168,6 +189,32 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
         uint32_t wc0 = 0;                                 // ring position of the conv's tap 0
         const int t0 = jw, t1 = L2_PH0_TILES + (jw + 1) % 3;                 // this warp's tile of phase 0 (jw < 2 only) and of phase 1
         for (int k = 0; k < n_my; ++k) {
+            if (MODE == 1) {
+                // ---- m_up2's transposed conv: two M128 N256 tiles (coarse rows 0..255), K = 128 in 8 steps, D over all 512 columns ----
+                mbar_wait(bar(L2B_X_FULL), (uint32_t)(k & 1));               // the coarse map is in T
+                wait_tiles(0, L2_TILES - 1, 4 * k - 1);                      // accumulators, lo stream and X of the previous item are dead
+                tc_fence_after();
+                const uint32_t idesc_u = instr_desc_f16(MTILE, L2_UN);
+                const uint64_t au0 = smem_desc(smem_u32(smem) + 8 * L2_PSTRIDE * 16, L2_DS * 16, 128) + (uint64_t)(uint32_t)(jw * MTILE);
+                const uint64_t wu0 = smem_desc(smem_u32(w_smem), L2_UN * 16, 128);
+                for (int i = 0; i < L2_USTAGES; ++i) {
+                    const uint32_t w = wc0 + (uint32_t)i, st = w % L2_WSTAGES;
+                    mbar_wait(bar(L2B_W_FULL + st), (w / L2_WSTAGES) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        if (jw < 2) {
+                            const uint64_t ad = au0 + (uint64_t)(uint32_t)(i * 2 * L2_DS), wd = wu0 + (uint64_t)(st * (L2_WSTAGE >> 4));
+                            if (i == 0) tc_mma_f16(tmem + (uint32_t)(jw * L2_UN), ad, wd, idesc_u, 0u);
+                            else tc_mma_f16_acc(tmem + (uint32_t)(jw * L2_UN), ad, wd, idesc_u);
+                        }
+                        tc_commit(bar(L2B_W_EMPTY + st));
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) tc_commit(bar(L2B_DOWN_FULL));              // (mode 1: "transposed conv issued and complete")
+                __syncwarp();
+                wc0 += L2_USTAGES;
+            }
             for (int c = 0; c < 4; ++c, wc0 += 9) {
                 const int n = 4 * k + c;
                 const int src_pl = (c & 1) ? 8 : 0;
@@ -185,15 +232,19 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
                 // input rows written back (tile t reads the rows of tiles t-1 .. t+1) and accumulators drained: tiles 0..2 for phase 0
                 wait_tiles(0, L2_PH0_TILES, n - 1);
                 if (c == 0) {
-                    mbar_wait(bar(L2B_X_FULL), (uint32_t)(k & 1));
-                    if (MODE == 0) mbar_wait(bar(L2B_DOWN_EMPTY), (uint32_t)((k & 1) ^ 1));    // the previous item's strided-conv accumulators are drained
+                    if (MODE == 0) {
+                        mbar_wait(bar(L2B_X_FULL), (uint32_t)(k & 1));
+                        mbar_wait(bar(L2B_DOWN_EMPTY), (uint32_t)((k & 1) ^ 1));    // the previous item's strided-conv accumulators are drained
+                    } else {
+                        mbar_wait(bar(L2B_DOWN_EMPTY), (uint32_t)(k & 1));          // this item's transposed conv: hi scattered into X, D drained
+                    }
                 }
                 tc_fence_after();
                 constexpr int LAG = L2_LAG;
                 for (int i = 0; i < 9 + LAG; ++i) {
                     if (i == LAG) {                    // ... tiles 3, 4 for phase 1
                         wait_tiles(L2_PH0_TILES + 1, L2_TILES - 1, n - 1);
-                        if (c == 0) mbar_wait(bar(L2B_X_FULL + 1), (uint32_t)(k & 1));
+                        if (MODE == 0 && c == 0) mbar_wait(bar(L2B_X_FULL + 1), (uint32_t)(k & 1));
                         tc_fence_after();
                     }
                     if (i < 9) {
@@ -256,10 +307,48 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         for (int k = 0; k < n_my; ++k) {
             const int b = (int)blockIdx.x + k * (int)gridDim.x;
+            uint4* scr = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(p.scratch) + (size_t)blockIdx.x * L2_SCRATCH_BYTES);
+            if (MODE == 1) {
+                // ---- transposed-conv epilogue: unit = (tile, sub-pixel): 64 channels of fine pixel (2cy+dy, 2cx+dx) per coarse row.  hi ->
+                // X (the operand of conv 0), lo -> this CTA's scratch (L2), from where the helper warps below move it to tensor memory ----
+                mbar_wait(bar(L2B_DOWN_FULL), (uint32_t)(k & 1));
+                tc_fence_after();
+                for (int u = grp; u < 8; u += L2_EPI_GROUPS) {
+                    const int j = u >> 2, sp = u & 3;
+                    const int cr = j * MTILE + q * 32 + lane, cy = (cr * 5042) >> 16, cx = cr - cy * 13;        // cr / 13 exactly for cr < 256
+                    const bool ok = cr < 156 && cx < 12;
+                    const int s = (2 * cy + (sp >> 1)) * L2_WP + 2 * cx + (sp & 1);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const uint32_t a = tmem + lane_base + (uint32_t)(j * L2_UN + sp * L2_C + hf * 32);
+                        uint32_t d0[16], d1[16];
+                        tc_ld16_nowait(a, d0); tc_ld16_nowait(a + 16, d1);
+                        tc_ld_wait16(d0); tc_ld_wait16(d1);
+                        if (ok) {
+                            float v[32];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(d0[i]); v[16 + i] = __uint_as_float(d1[i]); }
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch) {
+                                uint4 hi8, lo8;
+                                split8_hilo(v + 8 * ch, hi8, lo8);
+                                *reinterpret_cast<uint4*>(smem + row_off(4 * hf + ch, s)) = hi8;
+                                __stcg(scr + (4 * hf + ch) * L2_S + s, lo8);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(L2B_DOWN_EMPTY));
+            }
             if (warp < 8) {
-                if (MODE == 0 && k > 0) {
-                    // the strided conv's operand overwrote ALL of T: restore the never-written zero rows (gap above each plane, pad column,
-                    // zero rows below the stamp) before this item's conv 1 reads T; the valid rows are rewritten by conv 0's epilogue
+                if (MODE == 1) mbar_wait(bar(L2B_DOWN_EMPTY), (uint32_t)(k & 1));   // every warp has read D (the lo columns are part of it) and written its lo halves
+                if (MODE == 1 || k > 0) {
+                    // the strided conv's operand (DOWN) / the transposed conv's input (UP) overwrote T: restore the never-written zero rows (gap
+                    // above each plane, pad column, zero rows below the stamp) before this item's conv 1 reads T; the valid rows are
+                    // rewritten by conv 0's epilogue
                     for (int i = (warp - 4) * 32 + lane; i < 8 * 96 + L2_GAP; i += 128) {
                         int pl, s;
                         if (i < 8 * 96) {
@@ -276,9 +365,16 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_l2_chain(const L2ChainParams 
                 for (int t = 0; t < L2_TILES; ++t) {
                     const int s = t * MTILE + q * 32 + lane;
                     uint4 lo[8];
+                    if (MODE == 1) {
+                        const int yy = (s * 2622) >> 16;
+                        const bool ok = s < L2_PIX && s - yy * L2_WP < 24;       // pad rows of the scratch are never written
 #pragma unroll
-                    for (int ch = 0; ch < 8; ++ch)
-                        lo[ch] = s < L2_S ? __ldg(lo_g + (size_t)ch * Ptot1 + s) : make_uint4(0u, 0u, 0u, 0u);
+                        for (int ch = 0; ch < 8; ++ch) lo[ch] = ok ? __ldcg(scr + ch * L2_S + s) : make_uint4(0u, 0u, 0u, 0u);
+                    } else {
+#pragma unroll
+                        for (int ch = 0; ch < 8; ++ch)
+                            lo[ch] = s < L2_S ? __ldg(lo_g + (size_t)ch * Ptot1 + s) : make_uint4(0u, 0u, 0u, 0u);
+                    }
                     const uint32_t taddr = tmem + lane_base + (uint32_t)(L2_LO_COL + t * 32);
                     tc_st16(taddr, reinterpret_cast<const uint32_t*>(lo));
                     tc_st16(taddr + 16, reinterpret_cast<const uint32_t*>(lo) + 16);
@@ -424,21 +520,26 @@ int conv_l2chain_init() {
     return GD_OK;
 }
 
+size_t l2chain_scratch_bytes() { return (size_t)160 * L2_SCRATCH_BYTES; }      // one region per CTA of the persistent grid (<= 160 SMs)
+
+// mode 0 (m_down2): x_hi / x_lo = the level's input stream; wdown, skip3, x3_16 = the strided conv and its outputs.
+// mode 1 (m_up2):   a_coarse = fp16 input of the transposed conv (level 2), wup its weights, scratch; skip32 = x2, out16 = fp16 (x + x2).
 int launch_l2chain(int mode, const Geom& g1, const Geom& g2, int nb, const void* x_hi, const void* x_lo, const void* const* w4, const void* wdown,
-                   float* skip3, void* x3_16, const float* skip32, void* out16, cudaStream_t st) {
+                   float* skip3, void* x3_16, const void* a_coarse, const void* wup, void* scratch, const float* skip32, void* out16, cudaStream_t st) {
     if (nb <= 0) return GD_OK;
     if (!g_l2_sms) { set_error("conv_l2chain: library not initialised"); return GD_ECUDA; }
     if (g1.Wp != L2_WP || g1.S != L2_S || g2.Wp != 13 || g2.S != L2_DS) { set_error("conv_l2chain: needs the 24x24 / 12x12 geometries"); return GD_EUNSUPPORTED; }
     L2ChainParams p;
     memset(&p, 0, sizeof(p));
-    p.nb = nb; p.mode = mode; p.g1 = g1; p.g2 = g2; p.x_hi = x_hi; p.x_lo = x_lo; p.wdown = wdown; p.skip3 = skip3; p.x3_16 = x3_16; p.skip32 = skip32; p.out16 = out16;
+    p.nb = nb; p.mode = mode; p.g1 = g1; p.g2 = g2; p.x_hi = x_hi; p.x_lo = x_lo; p.wdown = wdown; p.skip3 = skip3; p.x3_16 = x3_16; p.a_coarse = a_coarse; p.wup = wup; p.scratch = scratch; p.skip32 = skip32; p.out16 = out16;
     for (int i = 0; i < 4; ++i) p.w[i] = w4[i];
-    if (!x_hi || !x_lo || !w4[0] || !w4[1] || !w4[2] || !w4[3] || (mode == 0 ? (!wdown || !skip3 || !x3_16) : (!skip32 || !out16))) {
+    if (!w4[0] || !w4[1] || !w4[2] || !w4[3] ||
+        (mode == 0 ? (!x_hi || !x_lo || !wdown || !skip3 || !x3_16) : (!a_coarse || !wup || !scratch || !skip32 || !out16)) || g_l2_sms > 160) {
         set_error("conv_l2chain: missing buffer"); return GD_EBADSHAPE;
     }
     const int grid = nb < g_l2_sms ? nb : g_l2_sms;
     cudaEvent_t e1 = nullptr;
-    const double flops = 4.0 * 2.0 * (double)nb * 576 * (double)L2_C * L2_C * 9 + (mode == 0 ? 2.0 * (double)nb * 144 * 256 * L2_DN : 0.0);
+    const double flops = 4.0 * 2.0 * (double)nb * 576 * (double)L2_C * L2_C * 9 + (mode == 0 ? 2.0 * (double)nb * 144 * 256 * L2_DN : 2.0 * (double)nb * 144 * 128 * L2_UN);
     { int rc = conv_profile_mark(flops, st, &e1); if (rc != GD_OK) return rc; }
     if (mode == 0) k_l2_chain<0><<<grid, L2_THREADS, L2_SMEM, st>>>(p);
     else k_l2_chain<1><<<grid, L2_THREADS, L2_SMEM, st>>>(p);

@@ -20,8 +20,9 @@ size_t l1chain_scratch_bytes();
 int launch_l1chain_up(const Geom& g0, const Geom& g1, int nb, const void* x_in, const void* wup, const float* tail_w_host, const void* const* w4,
                       float* tail_part, void* scratch, cudaStream_t st);
 int conv_l2chain_init();
+size_t l2chain_scratch_bytes();
 int launch_l2chain(int mode, const Geom& g1, const Geom& g2, int nb, const void* x_hi, const void* x_lo, const void* const* w4, const void* wdown,
-                   float* skip3, void* x3_16, const float* skip32, void* out16, cudaStream_t st);
+                   float* skip3, void* x3_16, const void* a_coarse, const void* wup, void* scratch, const float* skip32, void* out16, cudaStream_t st);
 bool conv_rb_supported(const ConvParams& p1, const ConvParams& p2);
 int launch_conv_rb(const ConvParams& p1, const ConvParams& p2, cudaStream_t st);
 
