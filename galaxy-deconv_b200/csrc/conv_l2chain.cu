@@ -1,13 +1,15 @@
 // Level-1 chain kernel of the ResUNet denoiser (64 channels at 24x24, path G: models/ResUNet.py:33 and :37), tcgen05 path:
-// the two ResBlocks of m_down2 resp. m_up2 (four 3x3 convolutions, models/resnet_basicblock.py:69-71) in ONE launch per stage,
-// with every intermediate on chip.  One launch per conv moves the fp16 hi/lo stream through HBM around every ResBlock and
-// runs the residual-carrying second convs at the HBM roofline (5.7 TB/s, profiles/layers_r02.csv); here a work item is ONE
-// WHOLE STAMP (625 padded-linear rows = 5 tiles of 128, no halo to recompute), so HBM sees the stream once per stage.
+// DOWN = the two ResBlocks of m_down2 + its k2s2 strided conv, UP = the k2s2 transposed conv of m_up2 + its two ResBlocks + the
+// U-Net skip (four 3x3 convolutions, models/resnet_basicblock.py:69-71, and one 1-tap GEMM) in ONE launch per stage, with every
+// intermediate on chip.  One launch per conv moves the fp16 hi/lo stream through HBM around every ResBlock and runs the
+// residual-carrying second convs at the HBM roofline; here a work item is ONE WHOLE STAMP (625 padded-linear rows = 5 tiles of 128,
+// no halo to recompute), so HBM sees the stage's input and output once.
 //
 //   * the fp16 operand copies of the stream (X) and of ReLU(conv1) (T) live in shared memory: 2 x 8 chunk planes x 672 rows x 16 B;
 //     rows 625..671 of a plane are never written (zero row below the stamp + gap absorbing the tap shifts);
 //   * the residual stream is hi + lo: hi = the operand copy in X, lo = rn16(x - hi) packed two per column in TENSOR MEMORY
-//     (5 tiles x 32 columns) -- |x - (hi + lo)| <= 2^-22 |x| as in the HBM stream of the other levels;
+//     (5 tiles x 32 columns) -- |x - (hi + lo)| <= 2^-22 |x| as in the HBM stream of the other levels; the helper warps bring the lo
+//     halves of an item straight from global memory (DOWN) or from this CTA's scratch (UP) into tensor memory;
 //   * a conv's weights (74 KB) do not fit beside X and T, so the MMA loop is TAP-OUTER: the five tiles' accumulators (5 x 64 TMEM
 //     columns) are live together and each of the nine 8 KB tap slices streams ONCE per conv and stamp through a 7-stage ring;
 //   * to let a conv's epilogue overlap MMAs although every tile completes with the last tap, the tiles form two phases on the same
@@ -16,13 +18,21 @@
 //     drain.  Streaming the ring once per phase instead (no lag) starves the MMAs: 48 KB in flight cover < 1 us of phase-0 issue.
 //     Measured on one box (G(8), 10,000 stamps): no lag 57.3 k gal/s, lag 3 57.9 k, lag 4 58.1 k; without this kernel 55.4 k.
 //   * the N = 64 MMA reads 4 KB of A and 2 KB of B from shared memory: 48 cycles at 128 B/cycle against 32 cycles of math, so the
-//     tensor pipe cannot exceed 67 % here; the kernel runs at ~58 cycles per MMA while issuing (46 % over the launch,
-//     profiles/l2chain_stalls_r02.txt).
+//     tensor pipe cannot exceed 67 % here; the kernel runs at ~58 cycles per MMA while issuing;
+//   * DOWN ends with the strided conv (64 -> 128 channels at 12x12): the last epilogue writes its space-to-depth operand
+//     [32][169][8] over the T planes (which it fills exactly) instead of HBM, two M128 N128 K256 tiles reuse the accumulator columns,
+//     a fifth epilogue stores x3 (fp32 skip + fp16 operand copy); the helper warps restore T's zero rows for the next item.
+//     1.00 + 0.29 ms (chain + separate launch) -> 1.08 ms per 5000 stamps, 58.3 k -> 59.6 k gal/s;
+//   * UP starts with the transposed conv (128 -> 4 x 64 channels): the coarse map [16][169][8] is bulk-copied into the T planes,
+//     two M128 N256 K128 tiles fill ALL 512 tensor-memory columns (the lo stream does not exist yet), the epilogue scatters the hi
+//     halves of the four sub-pixels straight into X and passes the lo halves through a per-CTA, L2-resident scratch (a thread can
+//     only write its own TMEM lane).  1.02 + 0.29 ms -> 1.27 ms: the drain per item (A load, 16 MMAs, scatter, scratch -> TMEM)
+//     costs nearly what the launch did, but 0.74 GB of fine-level hi/lo traffic per call is gone; 59.6 k -> 60.2 k gal/s.
 //
-// Warp roles (512 threads, one persistent CTA per SM): warp 0 producers (lane 0: tap slices; lane 1: hi -> X in two row ranges,
-// lo -> T, L2 prefetch of the next item), warps 1-3 MMA issue (one thread sustains only ~1 tcgen05.mma per 57 cycles), warps 4-15
-// epilogue in three groups of four quadrant warps (unit = tile x 32-channel half, round robin); warps 4-7 first move the lo halves
-// of the item's input stream from T to tensor memory.
+// Warp roles (512 threads, one persistent CTA per SM): warp 0 producers (lane 0: tap slices and the k2s2 weights; lane 1: DOWN: hi ->
+// X in two row ranges, L2 prefetch of the next item; UP: coarse map -> T), warps 1-3 MMA issue (one thread sustains only ~1
+// tcgen05.mma per 57 cycles), warps 4-15 epilogue in three groups of four quadrant warps (unit = tile x 32-channel half, round
+// robin); warps 4-7 also move the lo halves of the item's input stream to tensor memory.
 #include "conv_epilogue.cuh"
 #include "kernels.cuh"
 #include "launch.cuh"
