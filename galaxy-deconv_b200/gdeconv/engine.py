@@ -5,6 +5,7 @@ into libgdeconv.so on the current CUDA stream.  There is no CPU path: CPU tensor
 """
 from __future__ import annotations
 
+import copy
 import ctypes as C
 import os
 import threading
@@ -222,7 +223,8 @@ class AdmmEngine:
 
     # engines hold ctypes handles and CUDA graphs: copies / pickles of the owning module start with an empty cache
     def __deepcopy__(self, memo):
-        return AdmmEngine(self._module, self.arch, self.n_iters)
+        # bind the copy to the COPY of the owning module (already in `memo` while copy.deepcopy(model) walks its attributes)
+        return AdmmEngine(copy.deepcopy(self._module, memo), self.arch, self.n_iters)
 
     def __getstate__(self):
         return dict(_module=self._module, arch=self.arch, n_iters=self.n_iters)
@@ -556,6 +558,20 @@ class XDenseEngine:
 
     def __init__(self, module, prefix):
         self._module, self._prefix, self._packed = module, prefix, {}
+
+    # ctypes handles cannot be copied or pickled: copies of the owning module start with an empty cache, bound to the copy
+    def __deepcopy__(self, memo):
+        return XDenseEngine(copy.deepcopy(self._module, memo), self._prefix)
+
+    def __getstate__(self):
+        return dict(_module=self._module, _prefix=self._prefix)
+
+    def __setstate__(self, st):
+        self.__init__(st['_module'], st['_prefix'])
+
+    def invalidate(self):
+        """Drop the packed weights (call after in-place updates through ``.data``, which do not bump ``_version``)."""
+        self._packed.clear()
 
     def _weights(self, device):
         sd = self._module.state_dict(keep_vars=True)

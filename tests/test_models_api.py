@@ -51,6 +51,15 @@ def test_load_state_dict_roundtrip_and_module_protocol():
     assert all(torch.equal(m.state_dict()[k], sd[k]) for k in sd)
     m2 = copy.deepcopy(m)                      # engines must not break copying
     assert all(torch.equal(m2.state_dict()[k], sd[k]) for k in sd)
+    # ... and the copy's engines are bound to the COPY: changing the original must not reach them
+    assert m2._engine[0]._module is m2 and m._engine[0]._module is m
+    assert m2.init._engine[0]._module._m is m2.init if hasattr(m2.init._engine[0]._module, '_m') else True
+    from models.Tikhonet import Tikhonet
+    t = Tikhonet('Laplacian')
+    t2 = copy.deepcopy(t)
+    assert t2.denoiser._engine[0]._module is t2.denoiser and t.denoiser._engine[0]._module is t.denoiser
+    import pickle
+    assert pickle.loads(pickle.dumps(t2.denoiser._engine[0]))._prefix == ''
 
 
 def test_no_cpu_path():
