@@ -200,6 +200,9 @@ static int init_once(int device) {
     return GD_OK;
 }
 
+// for the entry points that live in other translation units (xdense.cu): the device's kernels get their launch attributes here
+namespace gd { int ensure_device_init(int device) { return init_once(device); } }
+
 extern "C" int gd_pack_weights(int arch, int n_iters, const GdTensorDesc* tensors, int n_tensors, int precision,
                                int device, GdWeights** out) {
     if (!out) GD_FAIL(GD_EBADSHAPE, "gd_pack_weights: out is NULL");

@@ -7,6 +7,7 @@
 namespace gd {
 
 int fft_kernels_init();
+int ensure_device_init(int device);      // api.cu: once per device, opt-in shared memory sizes etc. of every kernel
 int subnet_init();
 int conv_umma_init();
 void conv_profile_begin();

@@ -15,6 +15,7 @@
 // Kernels: k_xd_in (3x3 1->32), k_xd_dense (BN + ReLU + depthwise 3x3 + pointwise C->12, one launch per dense layer),
 // k_xd_pw (BN? + ReLU? + 1x1 conv (+bias) with three store modes: plain / 2x2 max-pool (Down) / nearest 2x up-sample (Up)).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -96,6 +97,91 @@ __global__ void __launch_bounds__(128) k_xd_dense(float* __restrict__ buf, int C
     float* out = base + (size_t)L.c_out0 * HW + p;
 #pragma unroll
     for (int o = 0; o < 12; ++o) out[(size_t)o * HW] = acc[o];
+}
+
+// ---- the same dense layer for the two large resolutions (48x48, 24x24: 85 % of the dense-layer work), tiled through shared memory.
+// k_xd_dense above reloads and re-activates the 9 neighbours of every pixel and channel from global memory and fetches 23 weights per
+// channel with uniform global loads: ~70 instructions per pixel and channel, bound by load latency.  Here a CTA owns a band of TR
+// rows of one stamp, 8 input channels at a time are activated ONCE into a zero-bordered tile, the chunk's weights sit in shared
+// memory, and a thread produces PX horizontally adjacent pixels from a 3 x (PX + 2) window: ~35 instructions per pixel and channel
+// (the tile <-> image index decode is hoisted out of the channel loop: with it inside, the fill cost as much as the layer itself).
+// The arithmetic (and its order) is k_xd_dense's, so the two kernels agree bit for bit (tools/gpu/xd_ab.py).  GDECONV_XD_TILED=0
+// restores k_xd_dense everywhere.
+template <int H, int PX, int TR>
+__global__ void __launch_bounds__(128) k_xd_dense_tiled(float* __restrict__ buf, int Ctot, XdDense L) {
+    constexpr int HW = H * H, RS = H + 2, TROWS = TR + 2, TILE = TROWS * RS, TPR = H / PX, NACT = TR * TPR, CHK = 8;
+    static_assert(H % PX == 0 && H % TR == 0 && NACT <= 128, "band geometry");
+    __shared__ float tile[CHK * TILE];
+    __shared__ __align__(16) float wsm[CHK * 24];          // per channel: dw[9], 3 pad, pw[12]
+    const int b = blockIdx.y, y0 = blockIdx.x * TR, tid = threadIdx.x;
+    const int r = tid / TPR, x0 = (tid - r * TPR) * PX;
+    const bool active = tid < NACT;
+    float acc[PX][12];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+        for (int o = 0; o < 12; ++o) acc[p][o] = 0.f;
+    // this thread's elements of the activated tile (the same for every channel): tile index tid + 128 i <-> image pixel, decoded once
+    constexpr int NSLOT = (TILE + 127) / 128;
+    int slot_off[NSLOT];
+    bool slot_in[NSLOT], slot_ok[NSLOT];
+#pragma unroll
+    for (int i = 0; i < NSLOT; ++i) {
+        const int e = tid + 128 * i, rr = e / RS, cc = e - rr * RS, y = y0 + rr - 1, x = cc - 1;
+        slot_in[i] = e < TILE;
+        slot_ok[i] = slot_in[i] && y >= 0 && y < H && x >= 0 && x < H;
+        slot_off[i] = slot_ok[i] ? y * H + x : 0;
+    }
+    float* base = buf + (size_t)b * Ctot * HW;
+    const float* in = base + (size_t)L.c_in0 * HW;
+    for (int c0 = 0; c0 < L.C_in; c0 += CHK) {
+        const int n = L.C_in - c0 < CHK ? L.C_in - c0 : CHK;
+        __syncthreads();                                   // the previous chunk's windows have been read
+        for (int i = tid; i < n * 24; i += 128) {
+            const int ch = i / 24, j = i - ch * 24;
+            wsm[i] = j < 9 ? L.dw[(c0 + ch) * 9 + j] : j < 12 ? 0.f : L.pw[(c0 + ch) * 12 + j - 12];
+        }
+        for (int ch = 0; ch < n; ++ch) {
+            const float s = L.scale[c0 + ch], sh = L.shift[c0 + ch];
+            const float* src = in + (size_t)(c0 + ch) * HW;
+            float* dst = tile + ch * TILE + tid;
+#pragma unroll
+            for (int i = 0; i < NSLOT; ++i) {
+                // BN(eval) + ReLU; 'same' padding pads AFTER the activation (border elements of the tile are stored as zeros)
+                if (slot_in[i]) dst[128 * i] = slot_ok[i] ? fmaxf(fmaf(src[slot_off[i]], s, sh), 0.f) : 0.f;
+            }
+        }
+        __syncthreads();
+        if (active) {
+            for (int ch = 0; ch < n; ++ch) {
+                const float* tw = tile + ch * TILE + r * RS + x0;
+                float a[3][PX + 2];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int j = 0; j < PX + 2; ++j) a[ky][j] = tw[ky * RS + j];
+                const float4* w4 = reinterpret_cast<const float4*>(wsm + ch * 24);
+                float w[24];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { const float4 t = w4[q]; w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w; }
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) d = fmaf(w[t], a[t / 3][p + t % 3], d);
+#pragma unroll
+                    for (int o = 0; o < 12; ++o) acc[p][o] = fmaf(w[12 + o], d, acc[p][o]);
+                }
+            }
+        }
+    }
+    if (active) {
+        float* out = base + (size_t)L.c_out0 * HW + (y0 + r) * H + x0;
+#pragma unroll
+        for (int o = 0; o < 12; ++o)
+#pragma unroll
+            for (int p = 0; p < PX; ++p) out[(size_t)o * HW + p] = acc[p][o];
+    }
 }
 
 // ---- 1x1 conv with optional BN+ReLU in front and pool / up-sample behind; OT output channels per thread ----
@@ -269,6 +355,8 @@ extern "C" GD_API int gd_pack_xdense(const GdTensorDesc* tensors, int n_tensors,
     if (rc) { delete X; return rc; }
     gd::DeviceScope scope(device);
     cudaError_t e = scope.err;
+    // Tikhonet's Tikhonov step (k_wiener48) needs its opt-in shared-memory size even when this is the first call of the process
+    if (e == cudaSuccess) { int irc = gd::ensure_device_init(device); if (irc != GD_OK) { delete X; return irc; } }
     if (e == cudaSuccess) e = cudaMalloc(&X->blob, B.h.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(X->blob, B.h.data(), B.h.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { gd::set_error("gd_pack_xdense: %s", cudaGetErrorString(e)); delete X; return GD_ECUDA; }
@@ -298,8 +386,12 @@ extern "C" GD_API size_t gd_xdense_workspace_bytes(int chunk) {
 static int xd_forward_chunk(const GdXDense* X, const float* in, float* out, const float* out_scale, int nb, float* const* buf, cudaStream_t st) {
     auto dense = [&](int blk, int b) -> int {
         const int H = XD_H[b], HW = H * H;
+        static int tiled = -1;
+        if (tiled < 0) { const char* e = getenv("GDECONV_XD_TILED"); tiled = e ? atoi(e) : 1; }
         for (const XdDense& L : X->dense[blk]) {
-            k_xd_dense<<<dim3((HW + 127) / 128, nb), 128, 0, st>>>(buf[b], XD_C[b], H, L);
+            if (tiled && H == 48) k_xd_dense_tiled<48, 3, 8><<<dim3(6, nb), 128, 0, st>>>(buf[b], XD_C[b], L);
+            else if (tiled && H == 24) k_xd_dense_tiled<24, 3, 12><<<dim3(2, nb), 128, 0, st>>>(buf[b], XD_C[b], L);
+            else k_xd_dense<<<dim3((HW + 127) / 128, nb), 128, 0, st>>>(buf[b], XD_C[b], H, L);
             GD_LAUNCHED();
         }
         return GD_OK;
@@ -355,6 +447,7 @@ static int xd_run(const GdXDense* X, int filter, float lam, const float* y, cons
     if (!X) XD_FAIL("XDenseUNet weights are NULL");
     if (batch < 0 || chunk < 1 || !ws || ws_bytes < gd_xdense_workspace_bytes(chunk)) { gd::set_error("XDenseUNet: workspace too small for chunk %d", chunk); return GD_EWORKSPACE; }
     GD_DEVICE_SCOPE(X->device);
+    { int irc = gd::ensure_device_init(X->device); if (irc != GD_OK) return irc; }
     float* base = (float*)ws;
     float* buf[XD_NBUF];
     for (int i = 0; i < XD_NBUF; ++i) { buf[i] = base; base += (size_t)chunk * xd_buf_floats(i); }

@@ -91,3 +91,24 @@ def test_tikhonet_identity_seeded_and_ragged_batches(golden, tik):
     with torch.no_grad():
         want = ref(b['obs'][idx].cpu(), b['psf'][idx].cpu(), b['alpha'][idx].cpu())
     assert rel_l2(big[idx].cpu(), want).max() < 2e-5
+
+
+@pytest.mark.gpu
+def test_tikhonet_is_the_first_call_of_a_process():
+    """The Tikhonov step of Tikhonet runs in k_wiener48, whose shared-memory size needs a per-device opt-in: it must be in place even when
+    gd_pack_xdense / gd_tikhonet_forward are the first library calls of the process (no ADMM model, no solver call before them)."""
+    import subprocess
+    import sys
+    child = (
+        "import os, sys, torch\n"
+        "ROOT = sys.argv[1]\n"
+        "sys.path[:0] = [os.path.join(ROOT, 'galaxy-deconv_b200'), ROOT]\n"
+        "from models.Tikhonet import Tikhonet\n"
+        "torch.manual_seed(1)\n"
+        "m = Tikhonet('Laplacian').eval().to('cuda:0')\n"
+        "g = torch.load(os.path.join(ROOT, 'tests', 'golden', 'golden_v1.pt'))['inputs']\n"
+        "out = m(g['y'][:3].to('cuda:0'), g['psf'][:3].to('cuda:0'), g['alpha'][:3].to('cuda:0'))\n"
+        "torch.cuda.synchronize()\n"
+        "print('FIRST-CALL-OK', bool(torch.isfinite(out).all()))\n")
+    r = subprocess.run([sys.executable, '-c', child, ROOT], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'FIRST-CALL-OK True' in r.stdout, r.stderr[-2000:]
